@@ -1,0 +1,131 @@
+"""oracle/solvers.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes loaders for the two CPU max-flow checkers:
+
+* ``solve_port``  -- oracle/bk_lattice.c, our C restatement of the reference BK solver
+                     (lib/maxflow/src/maxflow.cpp:118-604) on an implicit lattice;
+* ``solve_ref``   -- oracle/_ref/libbkref.so, the *unmodified* reference solver compiled from
+                     /root/reference by oracle/Makefile (present only where that build ran; the
+                     built .so travels to the GPU box).
+
+Both take the dict produced by ``oracle.energy_terms.build_problem`` and return
+``(flow, mask uint8[shape], times)``.  Only tests/, bench.py's cpu_baseline / ``--impl reference`` arm
+and __graft_entry__.smoke() may import this module.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PORT_SO = os.path.join(_HERE, "_build", "libbk_lattice.so")
+_REF_SO = os.path.join(_HERE, "_ref", "libbkref.so")
+
+_c_double_p = ctypes.POINTER(ctypes.c_double)
+_c_u8_p = ctypes.POINTER(ctypes.c_uint8)
+_c_i64_p = ctypes.POINTER(ctypes.c_int64)
+
+
+def build(ref=True):
+    """Compile the checkers (port always; the reference build only when /root/reference exists)."""
+    subprocess.check_call(["make", "-s", "-C", _HERE, "port"])
+    if ref and os.path.isdir("/root/reference/lib/maxflow/src"):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+
+
+def have_ref():
+    return os.path.exists(_REF_SO)
+
+
+_port = None
+_ref = None
+
+
+def _load_port():
+    global _port
+    if _port is None:
+        if not os.path.exists(_PORT_SO):
+            build(ref=False)
+        lib = ctypes.CDLL(_PORT_SO)
+        lib.bk_lattice_solve.restype = ctypes.c_int
+        lib.bk_lattice_solve.argtypes = [ctypes.c_int, _c_i64_p, ctypes.POINTER(_c_double_p),
+                                         ctypes.POINTER(_c_double_p), _c_double_p, ctypes.c_double,
+                                         _c_u8_p, _c_double_p, _c_double_p]
+        _port = lib
+    return _port
+
+
+def _load_ref():
+    global _ref
+    if _ref is None:
+        lib = ctypes.CDLL(_REF_SO)
+        lib.bkref_lattice_solve.restype = ctypes.c_int
+        lib.bkref_lattice_solve.argtypes = [ctypes.c_int, _c_i64_p, ctypes.POINTER(_c_double_p),
+                                            ctypes.POINTER(_c_double_p), _c_double_p, _c_double_p,
+                                            _c_u8_p, _c_u8_p, ctypes.c_int, _c_u8_p, _c_double_p,
+                                            _c_double_p]
+        _ref = lib
+    return _ref
+
+
+def _dptr(a):
+    return a.ctypes.data_as(_c_double_p) if a is not None else _c_double_p()
+
+
+def _axis_ptrs(arrs, ndim):
+    P = _c_double_p * ndim
+    if arrs is None:
+        return P(*[_c_double_p() for _ in range(ndim)]), []
+    keep = [numpy.ascontiguousarray(a, dtype=numpy.float64) for a in arrs]
+    return P(*[_dptr(a) for a in keep]), keep
+
+
+def solve_port(prob):
+    """BK restatement (oracle/bk_lattice.c) on a build_problem() dict."""
+    lib = _load_port()
+    shape = tuple(int(s) for s in prob["shape"])
+    ndim = len(shape)
+    n = int(numpy.prod(shape))
+    shp = (ctypes.c_int64 * ndim)(*shape)
+    wf, k1 = _axis_ptrs(prob["wf"], ndim)
+    wb, k2 = _axis_ptrs(prob["wb"], ndim)
+    tr = numpy.ascontiguousarray(prob["tr"], dtype=numpy.float64)
+    mask = numpy.empty(n, dtype=numpy.uint8)
+    flow = ctypes.c_double(0)
+    times = (ctypes.c_double * 2)()
+    rc = lib.bk_lattice_solve(ndim, shp, wf, wb, _dptr(tr), float(prob["flow_const"]),
+                              mask.ctypes.data_as(_c_u8_p), ctypes.byref(flow), times)
+    if rc != 0:
+        raise RuntimeError("bk_lattice_solve failed (%d)" % rc)
+    return flow.value, mask.reshape(shape), {"setup_s": times[0], "maxflow_s": times[1]}
+
+
+def solve_ref(prob, use_sum_edge=False):
+    """The real reference BK (oracle/_ref/libbkref.so), replaying the reference call sequence
+    regional -> boundary -> fg -> bg (generate.py:159-172)."""
+    lib = _load_ref()
+    shape = tuple(int(s) for s in prob["shape"])
+    ndim = len(shape)
+    n = int(numpy.prod(shape))
+    shp = (ctypes.c_int64 * ndim)(*shape)
+    wf, k1 = _axis_ptrs(prob["wf"], ndim)
+    wb, k2 = _axis_ptrs(prob["wb"], ndim)
+    src = prob.get("src")
+    snk = prob.get("snk")
+    if src is not None:
+        src = numpy.ascontiguousarray(src, dtype=numpy.float64)
+        snk = numpy.ascontiguousarray(snk, dtype=numpy.float64)
+    fg = numpy.ascontiguousarray(prob["fg"], dtype=numpy.uint8)
+    bg = numpy.ascontiguousarray(prob["bg"], dtype=numpy.uint8)
+    mask = numpy.empty(n, dtype=numpy.uint8)
+    flow = ctypes.c_double(0)
+    times = (ctypes.c_double * 3)()
+    rc = lib.bkref_lattice_solve(ndim, shp, wf, wb, _dptr(src), _dptr(snk),
+                                 fg.ctypes.data_as(_c_u8_p) if fg.any() else _c_u8_p(),
+                                 bg.ctypes.data_as(_c_u8_p) if bg.any() else _c_u8_p(),
+                                 1 if use_sum_edge else 0,
+                                 mask.ctypes.data_as(_c_u8_p), ctypes.byref(flow), times)
+    if rc != 0:
+        raise RuntimeError("bkref_lattice_solve: instance exceeds the reference's int32 ids (graph.h:62,82)")
+    return flow.value, mask.reshape(shape), {"fill_s": times[0], "maxflow_s": times[1], "readout_s": times[2]}
