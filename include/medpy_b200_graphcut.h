@@ -1,0 +1,190 @@
+/* medpy_b200_graphcut.h -- the drop-in boundary of the B200 voxel graph-cut path.
+ *
+ * C ABI (plain pointers and sizes, no torch / numpy / C++ types) of libmedpy_b200_gc.so.  It replaces,
+ * for the voxel path only, what the reference reaches through its Boost.Python extension
+ * `medpy.graphcut.maxflow` (lib/maxflow/src/wrapper.cpp:59-89,125-134; class GraphDouble =
+ * Pythongraph<double,double,double>, pythongraph.h:15-22) plus the per-edge / per-node Python loops that
+ * feed it (medpy/graphcut/energy_voxel.py:611-664, graph.py:310-380,532-552).  Instead of one FFI call per
+ * edge, a whole energy term crosses the boundary in one call and is evaluated by a CUDA kernel on the
+ * implicit 2*ndim-connected lattice; no edge list is ever materialised.
+ *
+ * Conventions
+ *   - every function returns an int status: MGC_OK (0) or a negative MGC_E_* code; the message for the
+ *     last failure on a handle is available from mgc_last_error() (never exit(), unlike graph.cpp:22);
+ *   - node id == C-order flat index over the logical shape (generate.py:170-172, energy_voxel.py:650-677);
+ *   - arrays are described by (pointer, dtype, byte strides over the logical shape); host pointers are only
+ *     borrowed for the duration of the call (copied to the device inside); MGC_MEM_DEVICE pointers must be
+ *     valid on the handle's device and are read on the handle's stream;
+ *   - all device memory is owned by the library; a handle is not thread-safe, distinct handles are
+ *     independent; the GIL can be released around every call;
+ *   - there is NO CPU solver behind this ABI: with no usable CUDA device mgc_create fails with
+ *     MGC_E_CUDA and nothing else works.
+ */
+#ifndef MEDPY_B200_GRAPHCUT_H
+#define MEDPY_B200_GRAPHCUT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGC_ABI_VERSION 1
+#define MGC_MAX_NDIM 4
+
+/* status codes */
+#define MGC_OK 0
+#define MGC_E_ARG (-1)     /* malformed argument (mirrors the reference's ValueError cases)     */
+#define MGC_E_CUDA (-2)    /* CUDA runtime failure / no device                                  */
+#define MGC_E_NOMEM (-3)   /* device allocation failed                                          */
+#define MGC_E_STATE (-4)   /* call not valid in the handle's current state                      */
+#define MGC_E_WEIGHT (-5)  /* an n-link weight <= 0 was produced (GCGraph.set_nweight, graph.py:436-437) */
+#define MGC_E_NOCONV (-6)  /* solver hit its iteration cap without converging                   */
+
+/* element types of input arrays */
+#define MGC_F32 0
+#define MGC_F64 1
+#define MGC_U8 2
+#define MGC_I16 3
+#define MGC_I32 4
+
+/* memory space of an input / output pointer */
+#define MGC_MEM_HOST 0
+#define MGC_MEM_DEVICE 1
+
+/* boundary terms: the eight energy_voxel.boundary_* functions (energy_voxel.py:68-516) */
+#define MGC_BOUNDARY_DIFFERENCE_LINEAR 0       /* energy_voxel.py:145-191 */
+#define MGC_BOUNDARY_DIFFERENCE_EXPONENTIAL 1  /* :241-302 */
+#define MGC_BOUNDARY_DIFFERENCE_DIVISION 2     /* :352-409 */
+#define MGC_BOUNDARY_DIFFERENCE_POWER 3        /* :457-516 */
+#define MGC_BOUNDARY_MAXIMUM_LINEAR 4          /* :68-116  */
+#define MGC_BOUNDARY_MAXIMUM_EXPONENTIAL 5     /* :194-238 */
+#define MGC_BOUNDARY_MAXIMUM_DIVISION 6        /* :305-349 (computes the *difference* variant, :347) */
+#define MGC_BOUNDARY_MAXIMUM_POWER 7           /* :412-454 */
+
+/* termtype (graph.h:57-61, wrapper.cpp:85-88) */
+#define MGC_SOURCE 0
+#define MGC_SINK 1
+
+typedef struct mgc_graph mgc_graph; /* opaque; replaces GraphDouble + GCGraph storage */
+
+typedef struct mgc_array {
+    const void* data;                    /* first element (logical index 0,...,0) */
+    int32_t dtype;                       /* MGC_F32 ... */
+    int32_t mem;                         /* MGC_MEM_HOST | MGC_MEM_DEVICE */
+    int64_t strides[MGC_MAX_NDIM];       /* BYTE strides over the logical shape (numpy .strides) */
+} mgc_array;
+
+typedef struct mgc_stats {
+    int64_t n_voxels;
+    int64_t push_sweeps;        /* push/relabel sweeps executed                     */
+    int64_t global_relabels;    /* exact backward BFS passes                        */
+    int64_t relabel_sweeps;     /* relaxation sweeps inside those                   */
+    int64_t kernel_launches;    /* every kernel this handle launched                */
+    int64_t active_last;        /* active voxels at the last check (0 = converged)  */
+    double ms_terms;            /* device ms: boundary + regional + marker kernels  */
+    double ms_solve;            /* device ms: init + push-relabel + global relabels */
+    double ms_readout;          /* device ms: mask + energy kernels                 */
+    double flow_const;          /* sum of the add_tweights minima (graph.h:423)     */
+    double energy;              /* value maxflow() returned                         */
+    int64_t device_bytes;       /* device memory held by the handle                 */
+} mgc_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------------- */
+
+/* Replaces GraphDouble(nodes, edges) + add_node(nodes) (graph.py:305-306; graph.cpp:11-31) for a lattice
+ * of logical shape `shape[ndim]`, 1 <= ndim <= 4.  `device` = CUDA ordinal (or -1 for the current one). */
+int mgc_create(int32_t ndim, const int64_t* shape, int32_t device, mgc_graph** out);
+/* Slab variant for the z-slab multi-GPU path: this handle owns planes [z0, z1) of axis 0 of the global
+ * lattice `shape` and keeps one ghost plane on each interior side. */
+int mgc_create_slab(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, int32_t device, mgc_graph** out);
+void mgc_destroy(mgc_graph* g); /* ~Graph (graph.cpp:34-43) */
+/* Graph::reset (graph.h:133): forget all weights, keep the allocation. */
+int mgc_reset(mgc_graph* g);
+const char* mgc_last_error(const mgc_graph* g); /* g may be NULL: last create() failure */
+int mgc_abi_version(void);
+/* Use an externally owned cudaStream_t (e.g. torch's current stream) for all work of this handle. */
+int mgc_set_stream(mgc_graph* g, void* cuda_stream);
+int mgc_synchronize(mgc_graph* g);
+
+/* ---- t-links -------------------------------------------------------------------------------------- */
+
+/* regional_probability_map (energy_voxel.py:33-65) -> set_tweights_all (graph.py:532-552) ->
+ * add_tweights(v, p*alpha, (1-p)*alpha) for every voxel (graph.h:415-425).  The products are formed in
+ * `compute_dtype` (MGC_F32 or MGC_F64) -- the dtype numpy's promotion gives `probability_map * alpha`
+ * (f32 map * Python float stays f32) -- and only then widened to double (graph.py:496-498). */
+int mgc_add_regional_probability(mgc_graph* g, const mgc_array* prob, double alpha, int32_t compute_dtype);
+/* Generic set_tweights_all: add_tweights(v, src[v], snk[v]); src/snk are arrays of doubles over the
+ * logical shape. */
+int mgc_add_tweights_dense(mgc_graph* g, const mgc_array* src, const mgc_array* snk);
+/* set_source_nodes / set_sink_nodes (graph.py:310-380) as called by graph_from_voxels
+ * (generate.py:169-172): add_tweights(v, 65535, 0) where fg != 0, THEN add_tweights(v, 0, 65535) where
+ * bg != 0.  Either array may be NULL.  dtype MGC_U8 (numpy bool_). */
+int mgc_add_markers(mgc_graph* g, const mgc_array* fg, const mgc_array* bg);
+
+/* ---- n-links -------------------------------------------------------------------------------------- */
+
+/* One of the eight boundary terms evaluated over the whole lattice (replaces the per-edge loop
+ * energy_voxel.py:660-664 -> GCGraph.set_nweight -> Graph::sum_edge graph.h:456-480): for every axis d and
+ * voxel pair (p, p+e_d):  w = g(|I_p - I_q|) or g(max(|I_p|,|I_q|)), w /= spacing[d] when spacing != NULL,
+ * cap(p->q) += w, cap(q->p) += w, all in float64.
+ *   sigma : ignored by the two linear terms.
+ *   norm  : linear terms only -- the normaliser max|grad| / |max-min| the host computed in the image's own
+ *           dtype (energy_voxel.py:99,174); pass NaN to have the device compute it (f32/f64 images).
+ * Returns MGC_E_WEIGHT if any produced weight is <= 0 (the reference raises ValueError there). */
+int mgc_add_boundary(mgc_graph* g, int32_t kind, const mgc_array* image, double sigma,
+                     const double* spacing, double norm);
+/* Dense n-links along one axis for user-written boundary terms: fwd/bwd are double arrays over the logical
+ * shape; entry p holds cap(p -> p+e_axis) / cap(p+e_axis -> p); entries on the last plane of `axis` are
+ * ignored.  Accumulates like sum_edge (graph.h:456-480); 0 leaves a pair untouched, negative values ->
+ * MGC_E_WEIGHT (the `<= 0` ValueError of GCGraph.set_nweight is raised by the host layer, graph.py:436-437). */
+int mgc_add_nweights_dense(mgc_graph* g, int32_t axis, const mgc_array* fwd, const mgc_array* bwd);
+
+/* ---- solve / read-out ----------------------------------------------------------------------------- */
+
+/* Graph::maxflow() (maxflow.cpp:471-604; wrapper.cpp:68): runs the lattice push-relabel to a maximum
+ * preflow and returns the min-cut energy INCLUDING the add_tweights constants, like the reference's `flow`.
+ * Idempotent after convergence. */
+int mgc_maxflow(mgc_graph* g, double* energy);
+/* Bulk form of the what_segment loop (bin/medpy_graphcut_voxel.py:177-181): out[v] = 0 if the voxel is in
+ * the SINK set else 1, C-order over the logical shape.  `mem` selects host or device destination. */
+int mgc_get_mask(mgc_graph* g, uint8_t* out, int32_t mem);
+/* Graph::what_segment(i) (graph.h:560-571): MGC_SINK or MGC_SOURCE (free nodes -> SOURCE). */
+int mgc_what_segment(mgc_graph* g, int64_t node, int32_t* segment);
+/* Graph::get_edge(i, j) (graph.h:482-497): current residual capacity of arc i->j, 0 if not lattice neighbours. */
+int mgc_get_edge(mgc_graph* g, int64_t i, int64_t j, double* cap);
+/* Graph::get_trcap(i) (graph.h:535-540): current residual terminal capacity (>0 source, <0 sink). */
+int mgc_get_trcap(mgc_graph* g, int64_t node, double* trcap);
+int mgc_get_node_num(const mgc_graph* g, int64_t* n);
+int mgc_get_arc_num(const mgc_graph* g, int64_t* n);
+int mgc_get_stats(const mgc_graph* g, mgc_stats* out);
+
+/* ---- z-slab multi-GPU stepping (driven by the host over NCCL) ------------------- */
+
+/* Number of elements of one border-plane message: the product of the extents of axes 1..ndim-1. */
+int mgc_slab_plane_elems(const mgc_graph* g, int64_t* n);
+/* Initialise the solver state (source-excess clamp, sink capacities) once all terms are in. */
+int mgc_slab_begin(mgc_graph* g);
+/* `n` local push/relabel sweeps. */
+int mgc_slab_push(mgc_graph* g, int32_t n);
+/* Pack the messages for the lower / upper neighbour into device buffers of plane_elems elements each:
+ * heights (int32) of my border plane and the flow (double) pushed across the border since the last pack.
+ * Pass NULL for a side without neighbour. */
+int mgc_slab_pack(mgc_graph* g, int32_t* h_lo, double* f_lo, int32_t* h_hi, double* f_hi);
+/* Apply the neighbours' messages: ghost-plane heights, and received flow added to excess and to the reverse
+ * residual of my border plane. */
+int mgc_slab_unpack(mgc_graph* g, const int32_t* h_lo, const double* f_lo, const int32_t* h_hi, const double* f_hi);
+/* Global relabel, distributed: (re)start a backward BFS from the sink ... */
+int mgc_slab_relabel_begin(mgc_graph* g);
+/* ... relax locally until nothing changes; *changed_out = 1 if any height changed in this call. */
+int mgc_slab_relabel_relax(mgc_graph* g, int32_t* changed_out);
+/* Voxels with excess > 0 and a finite label (owned planes only). */
+int mgc_slab_count_active(mgc_graph* g, int64_t* active_out);
+/* Finish: build the mask of the owned planes and this slab's share of the energy
+ * (flow absorbed by the owned sink links + owned add_tweights constants). */
+int mgc_slab_finish(mgc_graph* g, double* energy_part);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEDPY_B200_GRAPHCUT_H */

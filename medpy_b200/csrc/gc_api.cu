@@ -1,0 +1,911 @@
+// gc_api.cu -- C-ABI of libmedpy_b200_gc.so (include/medpy_b200_graphcut.h) and the host driver of the
+// lattice push-relabel solver.  sm_100a only; there is no CPU path: without a CUDA device every entry
+// point fails with MGC_E_CUDA.
+#include "../../include/medpy_b200_graphcut.h"
+#include "gc_common.cuh"
+#include "gc_terms.cuh"
+#include "gc_solver.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+// ---------------------------------------------------------------------------------------------------
+// device memory pool: graph_from_voxels creates a new graph per call (generate.py:120); handing freed
+// blocks to the next handle keeps cudaMalloc (milliseconds per GB) out of the steady state.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+std::mutex g_pool_mu;
+std::map<std::pair<int, size_t>, std::vector<void*>> g_pool;
+thread_local std::string g_create_error;
+
+size_t round_up(size_t b) { const size_t g = size_t(1) << 21; return (b + g - 1) / g * g; }
+
+cudaError_t pool_alloc(int dev, size_t bytes, void** out)
+{
+    bytes = round_up(bytes);
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        auto it = g_pool.find({dev, bytes});
+        if (it != g_pool.end() && !it->second.empty()) {
+            *out = it->second.back();
+            it->second.pop_back();
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) {
+        // release cached blocks and retry once
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (auto& kv : g_pool) if (kv.first.first == dev) { for (void* p : kv.second) cudaFree(p); kv.second.clear(); }
+        cudaGetLastError();
+        e = cudaMalloc(out, bytes);
+    }
+    return e;
+}
+
+void pool_free(int dev, size_t bytes, void* p)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_pool[{dev, round_up(bytes)}].push_back(p);
+}
+
+struct Buf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+size_t dtype_size(int dt)
+{
+    switch (dt) {
+        case MGC_F32: return 4;
+        case MGC_F64: return 8;
+        case MGC_U8: return 1;
+        case MGC_I16: return 2;
+        case MGC_I32: return 4;
+        default: return 0;
+    }
+}
+}  // namespace
+
+struct mgc_graph {
+    int device = 0;
+    int user_ndim = 0;
+    int nd = 3;             // canonical axes
+    int shift = 0;          // canonical axis = user axis + shift
+    int64_t user_shape[4] = {1, 1, 1, 1};
+    Lattice L{};
+    bool slab = false;
+    bool ghost_lo = false, ghost_hi = false;
+    int64_t global_dim0 = 0, z0 = 0, z1 = 0;
+
+    State<double> S{};
+    std::vector<Buf> owned_bufs;       // everything allocated from the pool
+    Buf scratch[3];                    // staged (contiguous) copies of input arrays
+    Buf raw;                           // raw span of a strided host array
+    uint8_t* mask_dev = nullptr;
+    double* partials = nullptr;        // per-block partial sums
+    unsigned n_partials = 0;
+    void* minmax_buf = nullptr;        // 3 x 1024 partial min/max/absmax
+    double* d_scalars = nullptr;       // [0] flow_const, [1] absorbed, [2..3] minmax out
+    int* d_flags = nullptr;            // [0] bad weight, [1] changed, [2] work
+    unsigned long long* d_count = nullptr;
+    int64_t device_bytes = 0;
+
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev[6] = {};
+
+    bool state_init = false;
+    bool solved = false;
+    bool has_nlinks = false;
+    double energy = 0.0;
+    std::vector<uint8_t> host_mask;
+    bool host_mask_valid = false;
+
+    // tuning
+    int sweeps_per_round = 32;
+    int relax_batch = 4;
+    int64_t max_rounds = 100000;
+
+    mgc_stats st{};
+    std::string err;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            g->err = std::string(#call) + ": " + cudaGetErrorString(_e);                           \
+            return MGC_E_CUDA;                                                                     \
+        }                                                                                          \
+    } while (0)
+
+#define FAIL(code, msg)                                                                            \
+    do {                                                                                           \
+        g->err = (msg);                                                                            \
+        return (code);                                                                             \
+    } while (0)
+
+inline unsigned nblocks(const mgc_graph* g) { return (g->L.n + 255u) / 256u; }
+
+int alloc_buf(mgc_graph* g, size_t bytes, void** out)
+{
+    void* p = nullptr;
+    cudaError_t e = pool_alloc(g->device, bytes, &p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        g->err = std::string("device allocation of ") + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e);
+        return MGC_E_NOMEM;
+    }
+    g->owned_bufs.push_back({p, bytes});
+    g->device_bytes += (int64_t)round_up(bytes);
+    *out = p;
+    return MGC_OK;
+}
+
+int ensure_scratch(mgc_graph* g, Buf& b, size_t bytes)
+{
+    if (b.bytes >= bytes) return MGC_OK;
+    if (b.p) { pool_free(g->device, b.bytes, b.p); g->device_bytes -= (int64_t)round_up(b.bytes); }
+    b.p = nullptr; b.bytes = 0;
+    void* p = nullptr;
+    cudaError_t e = pool_alloc(g->device, bytes, &p);
+    if (e != cudaSuccess) { cudaGetLastError(); g->err = "scratch allocation failed"; return MGC_E_NOMEM; }
+    b.p = p; b.bytes = bytes;
+    g->device_bytes += (int64_t)round_up(bytes);
+    return MGC_OK;
+}
+
+// Bring an input array into a C-contiguous device buffer over the local lattice.  Returns a device pointer
+// valid until the next stage_input on the same slot.
+template <typename E>
+int gather_launch(mgc_graph* g, const char* src, const Strides4& st, E* dst)
+{
+    if (g->nd == 3) k_gather<E, 3><<<nblocks(g), 256, 0, g->stream>>>(g->L, src, st, dst);
+    else            k_gather<E, 4><<<nblocks(g), 256, 0, g->stream>>>(g->L, src, st, dst);
+    g->st.kernel_launches++;
+    return MGC_OK;
+}
+
+int stage_input(mgc_graph* g, const mgc_array* a, int slot, const void** out)
+{
+    const size_t es = dtype_size(a->dtype);
+    if (!es) FAIL(MGC_E_ARG, "unsupported dtype");
+    if (!a->data) FAIL(MGC_E_ARG, "null array");
+    // canonical strides
+    Strides4 st{};
+    bool contiguous = true;
+    long long span = (long long)es;
+    long long expect = (long long)es;
+    for (int d = g->nd - 1; d >= 0; --d) {
+        long long s = 0;
+        int ud = d - g->shift;
+        if (ud >= 0) s = (long long)a->strides[ud];
+        if (g->L.dim[d] > 1) {
+            if (s <= 0) FAIL(MGC_E_ARG, "array strides must be positive (pass a contiguous copy)");
+            if (s != expect) contiguous = false;
+            span += (long long)(g->L.dim[d] - 1) * s;
+        } else {
+            s = 0;
+        }
+        st.s[d] = s;
+        expect *= g->L.dim[d];
+    }
+    const size_t bytes = (size_t)g->L.n * es;
+    if (contiguous && a->mem == MGC_MEM_DEVICE) { *out = a->data; return MGC_OK; }
+    int rc = ensure_scratch(g, g->scratch[slot], bytes);
+    if (rc) return rc;
+    if (contiguous) {
+        CK(cudaMemcpyAsync(g->scratch[slot].p, a->data, bytes, cudaMemcpyHostToDevice, g->stream));
+        *out = g->scratch[slot].p;
+        return MGC_OK;
+    }
+    const char* src = (const char*)a->data;
+    if (a->mem == MGC_MEM_HOST) {
+        rc = ensure_scratch(g, g->raw, (size_t)span);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(g->raw.p, a->data, (size_t)span, cudaMemcpyHostToDevice, g->stream));
+        src = (const char*)g->raw.p;
+    }
+    switch (a->dtype) {
+        case MGC_F32: gather_launch<float>(g, src, st, (float*)g->scratch[slot].p); break;
+        case MGC_F64: gather_launch<double>(g, src, st, (double*)g->scratch[slot].p); break;
+        case MGC_U8: gather_launch<uint8_t>(g, src, st, (uint8_t*)g->scratch[slot].p); break;
+        case MGC_I16: gather_launch<int16_t>(g, src, st, (int16_t*)g->scratch[slot].p); break;
+        case MGC_I32: gather_launch<int32_t>(g, src, st, (int32_t*)g->scratch[slot].p); break;
+    }
+    CK(cudaGetLastError());
+    *out = g->scratch[slot].p;
+    return MGC_OK;
+}
+
+int finish_flow_const(mgc_graph* g)
+{
+    k_sum_partials<<<1, 256, 0, g->stream>>>(g->partials, nblocks(g), g->d_scalars);
+    g->st.kernel_launches++;
+    CK(cudaGetLastError());
+    return MGC_OK;
+}
+
+void invalidate(mgc_graph* g)
+{
+    g->state_init = false;
+    g->solved = false;
+    g->host_mask_valid = false;
+}
+
+struct Timer {
+    mgc_graph* g;
+    double* acc;
+    Timer(mgc_graph* g_, double* acc_) : g(g_), acc(acc_) { cudaEventRecord(g->ev[0], g->stream); }
+    void stop_sync()
+    {
+        cudaEventRecord(g->ev[1], g->stream);
+        cudaEventSynchronize(g->ev[1]);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, g->ev[0], g->ev[1]);
+        *acc += ms;
+    }
+};
+
+int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool slab, int32_t device, mgc_graph** out)
+{
+    if (!out) return MGC_E_ARG;
+    *out = nullptr;
+    if (ndim < 1 || ndim > MGC_MAX_NDIM || !shape) { g_create_error = "ndim must be 1..4"; return MGC_E_ARG; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        g_create_error = std::string("no usable CUDA device (this library has no CPU path): ") + cudaGetErrorString(e);
+        return MGC_E_CUDA;
+    }
+    if (device < 0) cudaGetDevice(&device);
+    if (device >= ndev) { g_create_error = "bad device ordinal"; return MGC_E_ARG; }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return MGC_E_CUDA; }
+
+    mgc_graph* g = new mgc_graph();
+    g->device = device;
+    g->user_ndim = ndim;
+    g->nd = ndim == 4 ? 4 : 3;
+    g->shift = g->nd - ndim;
+    for (int d = 0; d < ndim; ++d) {
+        if (shape[d] < 1) { g_create_error = "extents must be >= 1"; delete g; return MGC_E_ARG; }
+        g->user_shape[d] = shape[d];
+    }
+    int64_t dims[4] = {1, 1, 1, 1};
+    for (int d = 0; d < ndim; ++d) dims[d + g->shift] = shape[d];
+    g->slab = slab;
+    int own0 = 0, own1 = (int)dims[0];
+    if (slab) {
+        if (g->shift != 0 || z0 < 0 || z1 > shape[0] || z0 >= z1) { g_create_error = "bad slab"; delete g; return MGC_E_ARG; }
+        g->global_dim0 = shape[0]; g->z0 = z0; g->z1 = z1;
+        g->ghost_lo = z0 > 0; g->ghost_hi = z1 < shape[0];
+        dims[0] = (z1 - z0) + (g->ghost_lo ? 1 : 0) + (g->ghost_hi ? 1 : 0);
+        own0 = g->ghost_lo ? 1 : 0;
+        own1 = own0 + (int)(z1 - z0);
+    }
+    int64_t n = 1;
+    for (int d = 0; d < g->nd; ++d) n *= dims[d];
+    if (n >= (int64_t(1) << 31)) { g_create_error = "lattice too large for one device handle (>= 2^31 voxels)"; delete g; return MGC_E_ARG; }
+    g->L.nd = g->nd;
+    unsigned s = (unsigned)n;
+    for (int d = 0; d < 4; ++d) { g->L.dim[d] = 1; g->L.stride[d] = 1; }
+    for (int d = 0; d < g->nd; ++d) { g->L.dim[d] = (int)dims[d]; s /= (unsigned)dims[d]; g->L.stride[d] = s; }
+    g->L.n = (unsigned)n;
+    g->L.plane = g->L.stride[0];
+    g->L.own0 = own0; g->L.own1 = own1;
+
+    int rc = MGC_OK;
+    const size_t nb = (size_t)n;
+    void* p = nullptr;
+    for (int k = 0; k < 2 * g->nd && !rc; ++k) { rc = alloc_buf(g, nb * sizeof(double), &p); g->S.cap[k] = (double*)p; }
+    if (!rc) { rc = alloc_buf(g, nb * sizeof(double), &p); g->S.excess = (double*)p; }
+    if (!rc) { rc = alloc_buf(g, nb * sizeof(double), &p); g->S.sink = (double*)p; }
+    if (!rc) { rc = alloc_buf(g, nb * sizeof(double), &p); g->S.tr = (double*)p; }
+    if (!rc) { rc = alloc_buf(g, nb * sizeof(int), &p); g->S.height = (int*)p; }
+    if (!rc) { rc = alloc_buf(g, nb, &p); g->S.rmask = (uint8_t*)p; }
+    if (!rc) { rc = alloc_buf(g, nb, &p); g->mask_dev = (uint8_t*)p; }
+    g->n_partials = nblocks(g);
+    if (!rc) { rc = alloc_buf(g, (size_t)g->n_partials * sizeof(double), &p); g->partials = (double*)p; }
+    if (!rc) { rc = alloc_buf(g, 3 * 1024 * sizeof(double), &p); g->minmax_buf = p; }
+    if (!rc) { rc = alloc_buf(g, 64, &p); g->d_scalars = (double*)p; }
+    if (!rc) { rc = alloc_buf(g, 64, &p); g->d_flags = (int*)p; }
+    if (!rc) { rc = alloc_buf(g, 64, &p); g->d_count = (unsigned long long*)p; }
+    if (rc) { g_create_error = g->err; mgc_destroy(g); return rc; }
+    if (cudaStreamCreate(&g->stream) != cudaSuccess) { g_create_error = "cudaStreamCreate failed"; mgc_destroy(g); return MGC_E_CUDA; }
+    g->own_stream = true;
+    for (auto& ev : g->ev) cudaEventCreate(&ev);
+    if (const char* s1 = getenv("MEDPY_GC_SWEEPS")) g->sweeps_per_round = atoi(s1) > 0 ? atoi(s1) : g->sweeps_per_round;
+    if (const char* s2 = getenv("MEDPY_GC_RELAX_BATCH")) g->relax_batch = atoi(s2) > 0 ? atoi(s2) : g->relax_batch;
+    g->st.n_voxels = (int64_t)n;
+    rc = mgc_reset(g);
+    if (rc) { g_create_error = g->err; mgc_destroy(g); return rc; }
+    *out = g;
+    return MGC_OK;
+}
+
+template <typename E>
+int boundary_launch(mgc_graph* g, const E* img, const BoundaryParams& P)
+{
+    if (g->nd == 3) k_boundary<E, 3, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, img, P, g->d_flags);
+    else            k_boundary<E, 4, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, img, P, g->d_flags);
+    g->st.kernel_launches++;
+    return MGC_OK;
+}
+
+template <typename E>
+int minmax_launch(mgc_graph* g, const E* img)
+{
+    unsigned nb = g->n_partials < 1024u ? g->n_partials : 1024u;
+    E* pm = (E*)g->minmax_buf;
+    E* px = pm + 1024;
+    E* pa = px + 1024;
+    k_minmax_partial<E><<<nb, 256, 0, g->stream>>>(img, g->L.n, pm, px, pa);
+    k_minmax_final<E><<<1, 32, 0, g->stream>>>(pm, px, pa, nb, g->d_scalars + 2);
+    g->st.kernel_launches += 2;
+    return MGC_OK;
+}
+
+int ensure_state(mgc_graph* g)
+{
+    if (g->state_init) return MGC_OK;
+    if (g->nd == 3) k_init_state<3, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S);
+    else            k_init_state<4, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S);
+    g->st.kernel_launches++;
+    CK(cudaGetLastError());
+    g->state_init = true;
+    return MGC_OK;
+}
+
+int relabel_init(mgc_graph* g)
+{
+    if (g->nd == 3) k_relabel_init<3, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S);
+    else            k_relabel_init<4, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S);
+    g->st.kernel_launches++;
+    CK(cudaGetLastError());
+    return MGC_OK;
+}
+
+// relax until a whole batch changes nothing; *any = 1 if anything changed at all
+int relabel_relax(mgc_graph* g, int* any)
+{
+    *any = 0;
+    for (;;) {
+        CK(cudaMemsetAsync(g->d_flags + 1, 0, sizeof(int), g->stream));
+        for (int i = 0; i < g->relax_batch; ++i) {
+            if (g->nd == 3) k_relabel_relax<3><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S.rmask, g->S.height, g->d_flags + 1);
+            else            k_relabel_relax<4><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S.rmask, g->S.height, g->d_flags + 1);
+        }
+        g->st.kernel_launches += g->relax_batch;
+        g->st.relabel_sweeps += g->relax_batch;
+        int changed = 0;
+        CK(cudaMemcpyAsync(&changed, g->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+        CK(cudaStreamSynchronize(g->stream));
+        if (!changed) break;
+        *any = 1;
+    }
+    return MGC_OK;
+}
+
+int count_active(mgc_graph* g, int64_t* out)
+{
+    CK(cudaMemsetAsync(g->d_count, 0, sizeof(unsigned long long), g->stream));
+    k_count_active<double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, g->d_count);
+    g->st.kernel_launches++;
+    unsigned long long c = 0;
+    CK(cudaMemcpyAsync(&c, g->d_count, sizeof(c), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    *out = (int64_t)c;
+    g->st.active_last = (int64_t)c;
+    return MGC_OK;
+}
+
+// n push sweeps; *work_last = whether the last sweep still found an active voxel
+int push_sweeps(mgc_graph* g, int n, int* work_last)
+{
+    for (int i = 0; i < n; ++i) {
+        if (i == n - 1) CK(cudaMemsetAsync(g->d_flags + 2, 0, sizeof(int), g->stream));
+        if (g->nd == 3) k_push<3, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, g->d_flags + 2);
+        else            k_push<4, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, g->d_flags + 2);
+    }
+    g->st.kernel_launches += n;
+    g->st.push_sweeps += n;
+    CK(cudaGetLastError());
+    if (work_last) {
+        CK(cudaMemcpyAsync(work_last, g->d_flags + 2, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+        CK(cudaStreamSynchronize(g->stream));
+    }
+    return MGC_OK;
+}
+
+int readout(mgc_graph* g, double* energy_part)
+{
+    k_mask<<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S.height, g->mask_dev);
+    k_absorbed<double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, g->partials);
+    CK(cudaMemsetAsync(g->d_scalars + 1, 0, sizeof(double), g->stream));
+    k_sum_partials<<<1, 256, 0, g->stream>>>(g->partials, nblocks(g), g->d_scalars + 1);
+    g->st.kernel_launches += 3;
+    double sc[2] = {0, 0};
+    CK(cudaMemcpyAsync(sc, g->d_scalars, sizeof(sc), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    g->st.flow_const = sc[0];
+    *energy_part = sc[0] + sc[1];
+    return MGC_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+int mgc_abi_version(void) { return MGC_ABI_VERSION; }
+
+const char* mgc_last_error(const mgc_graph* g) { return g ? g->err.c_str() : g_create_error.c_str(); }
+
+int mgc_create(int32_t ndim, const int64_t* shape, int32_t device, mgc_graph** out)
+{
+    return create_impl(ndim, shape, 0, 0, false, device, out);
+}
+
+int mgc_create_slab(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, int32_t device, mgc_graph** out)
+{
+    if (ndim < 3) { g_create_error = "z-slab handles need ndim >= 3"; return MGC_E_ARG; }
+    return create_impl(ndim, shape, z0, z1, true, device, out);
+}
+
+void mgc_destroy(mgc_graph* g)
+{
+    if (!g) return;
+    cudaSetDevice(g->device);
+    if (g->stream) cudaStreamSynchronize(g->stream);
+    for (auto& b : g->owned_bufs) pool_free(g->device, b.bytes, b.p);
+    for (auto& b : g->scratch) if (b.p) pool_free(g->device, b.bytes, b.p);
+    if (g->raw.p) pool_free(g->device, g->raw.bytes, g->raw.p);
+    for (auto& ev : g->ev) if (ev) cudaEventDestroy(ev);
+    if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
+    delete g;
+}
+
+int mgc_reset(mgc_graph* g)
+{
+    if (!g) return MGC_E_ARG;
+    CK(cudaSetDevice(g->device));
+    const size_t nb = (size_t)g->L.n;
+    for (int k = 0; k < 2 * g->nd; ++k) CK(cudaMemsetAsync(g->S.cap[k], 0, nb * sizeof(double), g->stream));
+    CK(cudaMemsetAsync(g->S.tr, 0, nb * sizeof(double), g->stream));
+    CK(cudaMemsetAsync(g->d_scalars, 0, 64, g->stream));
+    CK(cudaMemsetAsync(g->d_flags, 0, 64, g->stream));
+    invalidate(g);
+    g->has_nlinks = false;
+    g->energy = 0.0;
+    int64_t n = g->st.n_voxels;
+    g->st = mgc_stats{};
+    g->st.n_voxels = n;
+    return MGC_OK;
+}
+
+int mgc_set_stream(mgc_graph* g, void* cuda_stream)
+{
+    if (!g) return MGC_E_ARG;
+    CK(cudaStreamSynchronize(g->stream));
+    if (g->own_stream) { cudaStreamDestroy(g->stream); g->own_stream = false; }
+    g->stream = (cudaStream_t)cuda_stream;
+    return MGC_OK;
+}
+
+int mgc_synchronize(mgc_graph* g)
+{
+    if (!g) return MGC_E_ARG;
+    CK(cudaStreamSynchronize(g->stream));
+    return MGC_OK;
+}
+
+int mgc_add_regional_probability(mgc_graph* g, const mgc_array* prob, double alpha, int32_t compute_dtype)
+{
+    if (!g || !prob) return MGC_E_ARG;
+    if (prob->dtype != MGC_F32 && prob->dtype != MGC_F64) FAIL(MGC_E_ARG, "probability map must be float32 or float64");
+    if (compute_dtype != MGC_F32 && compute_dtype != MGC_F64) FAIL(MGC_E_ARG, "compute dtype must be float32 or float64");
+    CK(cudaSetDevice(g->device));
+    Timer t(g, &g->st.ms_terms);
+    const void* p = nullptr;
+    int rc = stage_input(g, prob, 0, &p);
+    if (rc) return rc;
+    if (prob->dtype == MGC_F32)
+        k_regional<float, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const float*)p, alpha, compute_dtype == MGC_F32, g->partials);
+    else
+        k_regional<double, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const double*)p, alpha, 0, g->partials);
+    g->st.kernel_launches++;
+    CK(cudaGetLastError());
+    rc = finish_flow_const(g);
+    if (rc) return rc;
+    invalidate(g);
+    t.stop_sync();
+    return MGC_OK;
+}
+
+int mgc_add_tweights_dense(mgc_graph* g, const mgc_array* src, const mgc_array* snk)
+{
+    if (!g || !src || !snk) return MGC_E_ARG;
+    if (src->dtype != MGC_F64 || snk->dtype != MGC_F64) FAIL(MGC_E_ARG, "dense t-weights must be float64");
+    CK(cudaSetDevice(g->device));
+    Timer t(g, &g->st.ms_terms);
+    const void *ps = nullptr, *pk = nullptr;
+    int rc = stage_input(g, src, 0, &ps);
+    if (rc) return rc;
+    rc = stage_input(g, snk, 1, &pk);
+    if (rc) return rc;
+    k_tweights_dense<double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const double*)ps, (const double*)pk, g->partials);
+    g->st.kernel_launches++;
+    CK(cudaGetLastError());
+    rc = finish_flow_const(g);
+    if (rc) return rc;
+    invalidate(g);
+    t.stop_sync();
+    return MGC_OK;
+}
+
+int mgc_add_markers(mgc_graph* g, const mgc_array* fg, const mgc_array* bg)
+{
+    if (!g) return MGC_E_ARG;
+    if (!fg && !bg) return MGC_OK;
+    if ((fg && fg->dtype != MGC_U8) || (bg && bg->dtype != MGC_U8)) FAIL(MGC_E_ARG, "markers must be uint8 / bool");
+    CK(cudaSetDevice(g->device));
+    Timer t(g, &g->st.ms_terms);
+    const void *pf = nullptr, *pb = nullptr;
+    int rc = MGC_OK;
+    if (fg) { rc = stage_input(g, fg, 0, &pf); if (rc) return rc; }
+    if (bg) { rc = stage_input(g, bg, 1, &pb); if (rc) return rc; }
+    k_markers<double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const uint8_t*)pf, (const uint8_t*)pb, g->partials);
+    g->st.kernel_launches++;
+    CK(cudaGetLastError());
+    rc = finish_flow_const(g);
+    if (rc) return rc;
+    invalidate(g);
+    t.stop_sync();
+    return MGC_OK;
+}
+
+int mgc_add_boundary(mgc_graph* g, int32_t kind, const mgc_array* image, double sigma, const double* spacing, double norm)
+{
+    if (!g || !image) return MGC_E_ARG;
+    if (kind < 0 || kind > 7) FAIL(MGC_E_ARG, "unknown boundary term");
+    CK(cudaSetDevice(g->device));
+    Timer t(g, &g->st.ms_terms);
+    const void* img = nullptr;
+    int rc = stage_input(g, image, 2, &img);
+    if (rc) return rc;
+    BoundaryParams P{};
+    P.fn = kind & 3;
+    // boundary_maximum_division computes the difference variant (energy_voxel.py:347)
+    P.use_max = (kind >= 4 && kind != MGC_BOUNDARY_MAXIMUM_DIVISION) ? 1 : 0;
+    P.sigma = (P.fn == 1) ? pow(sigma, 2) : sigma;   // math.pow(sigma, 2), energy_voxel.py:231
+    P.inv_spacing_on = spacing ? 1.0 : 0.0;
+    for (int d = 0; d < 4; ++d) P.spacing[d] = 1.0;
+    if (spacing) for (int d = 0; d < g->user_ndim; ++d) P.spacing[d + g->shift] = spacing[d];
+    P.norm = norm;
+    if (P.fn == 0 && std::isnan(norm)) {
+        if (g->slab) FAIL(MGC_E_ARG, "z-slab handles need the global normaliser of the linear terms");
+        switch (image->dtype) {
+            case MGC_F32: rc = minmax_launch<float>(g, (const float*)img); break;
+            case MGC_F64: rc = minmax_launch<double>(g, (const double*)img); break;
+            case MGC_U8: rc = minmax_launch<uint8_t>(g, (const uint8_t*)img); break;
+            case MGC_I16: rc = minmax_launch<int16_t>(g, (const int16_t*)img); break;
+            case MGC_I32: rc = minmax_launch<int32_t>(g, (const int32_t*)img); break;
+        }
+        if (rc) return rc;
+        double mm[2];
+        CK(cudaMemcpyAsync(mm, g->d_scalars + 2, sizeof(mm), cudaMemcpyDeviceToHost, g->stream));
+        CK(cudaStreamSynchronize(g->stream));
+        P.norm = (kind == MGC_BOUNDARY_MAXIMUM_LINEAR) ? mm[1] : mm[0];
+    }
+    CK(cudaMemsetAsync(g->d_flags, 0, sizeof(int), g->stream));
+    switch (image->dtype) {
+        case MGC_F32: boundary_launch<float>(g, (const float*)img, P); break;
+        case MGC_F64: boundary_launch<double>(g, (const double*)img, P); break;
+        case MGC_U8: boundary_launch<uint8_t>(g, (const uint8_t*)img, P); break;
+        case MGC_I16: boundary_launch<int16_t>(g, (const int16_t*)img, P); break;
+        case MGC_I32: boundary_launch<int32_t>(g, (const int32_t*)img, P); break;
+    }
+    CK(cudaGetLastError());
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, g->d_flags, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+    t.stop_sync();
+    invalidate(g);
+    g->has_nlinks = true;
+    if (bad) FAIL(MGC_E_WEIGHT, "Negative or zero weights are not allowed.");
+    return MGC_OK;
+}
+
+int mgc_add_nweights_dense(mgc_graph* g, int32_t axis, const mgc_array* fwd, const mgc_array* bwd)
+{
+    if (!g || !fwd || !bwd) return MGC_E_ARG;
+    if (axis < 0 || axis >= g->user_ndim) FAIL(MGC_E_ARG, "bad axis");
+    if (fwd->dtype != MGC_F64 || bwd->dtype != MGC_F64) FAIL(MGC_E_ARG, "dense n-weights must be float64");
+    CK(cudaSetDevice(g->device));
+    Timer t(g, &g->st.ms_terms);
+    const void *pf = nullptr, *pb = nullptr;
+    int rc = stage_input(g, fwd, 0, &pf);
+    if (rc) return rc;
+    rc = stage_input(g, bwd, 1, &pb);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(g->d_flags, 0, sizeof(int), g->stream));
+    const int ca = axis + g->shift;
+    if (g->nd == 3) k_nweights_dense<3, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, ca, (const double*)pf, (const double*)pb, g->d_flags);
+    else            k_nweights_dense<4, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, ca, (const double*)pf, (const double*)pb, g->d_flags);
+    g->st.kernel_launches++;
+    CK(cudaGetLastError());
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, g->d_flags, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+    t.stop_sync();
+    invalidate(g);
+    g->has_nlinks = true;
+    if (bad) FAIL(MGC_E_WEIGHT, "Negative or zero weights are not allowed.");
+    return MGC_OK;
+}
+
+int mgc_maxflow(mgc_graph* g, double* energy)
+{
+    if (!g) return MGC_E_ARG;
+    if (g->slab) FAIL(MGC_E_STATE, "z-slab handles are stepped with mgc_slab_*");
+    CK(cudaSetDevice(g->device));
+    if (g->solved) { if (energy) *energy = g->energy; return MGC_OK; }
+    {
+        Timer t(g, &g->st.ms_solve);
+        int rc = ensure_state(g);
+        if (rc) return rc;
+        int64_t rounds = 0;
+        for (;;) {
+            rc = relabel_init(g);
+            if (rc) return rc;
+            int any = 0;
+            rc = relabel_relax(g, &any);
+            if (rc) return rc;
+            g->st.global_relabels++;
+            int64_t active = 0;
+            rc = count_active(g, &active);
+            if (rc) return rc;
+            if (active == 0) break;
+            if (++rounds > g->max_rounds) FAIL(MGC_E_NOCONV, "push-relabel did not converge within the round cap");
+            // push sweeps until quiescent or the round budget is used
+            int done = 0;
+            while (done < g->sweeps_per_round) {
+                int chunk = g->sweeps_per_round - done;
+                if (chunk > 8) chunk = 8;
+                int work = 1;
+                rc = push_sweeps(g, chunk, &work);
+                if (rc) return rc;
+                done += chunk;
+                if (!work) break;
+            }
+        }
+        t.stop_sync();
+    }
+    {
+        Timer t(g, &g->st.ms_readout);
+        double e = 0.0;
+        int rc = readout(g, &e);
+        if (rc) return rc;
+        g->energy = e;
+        g->st.energy = e;
+        t.stop_sync();
+    }
+    g->solved = true;
+    if (energy) *energy = g->energy;
+    return MGC_OK;
+}
+
+int mgc_get_mask(mgc_graph* g, uint8_t* out, int32_t mem)
+{
+    if (!g || !out) return MGC_E_ARG;
+    if (!g->solved) FAIL(MGC_E_STATE, "call maxflow first");
+    CK(cudaSetDevice(g->device));
+    const size_t owned_n = (size_t)(g->L.own1 - g->L.own0) * g->L.plane;
+    const uint8_t* src = g->mask_dev + (size_t)g->L.own0 * g->L.plane;
+    CK(cudaMemcpyAsync(out, src, owned_n, mem == MGC_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    return MGC_OK;
+}
+
+int mgc_what_segment(mgc_graph* g, int64_t node, int32_t* segment)
+{
+    if (!g || !segment) return MGC_E_ARG;
+    if (!g->solved) FAIL(MGC_E_STATE, "call maxflow first");
+    if (node < 0 || node >= (int64_t)g->L.n) FAIL(MGC_E_ARG, "node id out of range");
+    if (!g->host_mask_valid) {
+        g->host_mask.resize(g->L.n);
+        CK(cudaMemcpyAsync(g->host_mask.data(), g->mask_dev, g->L.n, cudaMemcpyDeviceToHost, g->stream));
+        CK(cudaStreamSynchronize(g->stream));
+        g->host_mask_valid = true;
+    }
+    *segment = g->host_mask[(size_t)node] ? MGC_SOURCE : MGC_SINK;
+    return MGC_OK;
+}
+
+int mgc_get_edge(mgc_graph* g, int64_t i, int64_t j, double* cap)
+{
+    if (!g || !cap) return MGC_E_ARG;
+    const int64_t n = (int64_t)g->L.n;
+    if (i < 0 || j < 0 || i >= n || j >= n || i == j) FAIL(MGC_E_ARG, "bad node ids");
+    *cap = 0.0;
+    int c[4] = {0, 0, 0, 0};
+    unsigned r = (unsigned)i;
+    for (int d = 0; d < g->nd; ++d) { c[d] = (int)(r / g->L.stride[d]); r %= g->L.stride[d]; }
+    for (int k = 0; k < 2 * g->nd; ++k) {
+        const int d = k >> 1;
+        const int64_t off = (k & 1) ? (int64_t)g->L.stride[d] : -(int64_t)g->L.stride[d];
+        const int cn = c[d] + ((k & 1) ? 1 : -1);
+        if (cn < 0 || cn >= g->L.dim[d]) continue;
+        if (i + off == j) {
+            CK(cudaMemcpyAsync(cap, g->S.cap[k] + i, sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+            CK(cudaStreamSynchronize(g->stream));
+            return MGC_OK;
+        }
+    }
+    return MGC_OK;  // not lattice neighbours: 0, like get_edge on a missing arc (graph.h:482-497)
+}
+
+int mgc_get_trcap(mgc_graph* g, int64_t node, double* trcap)
+{
+    if (!g || !trcap) return MGC_E_ARG;
+    if (node < 0 || node >= (int64_t)g->L.n) FAIL(MGC_E_ARG, "node id out of range");
+    if (!g->state_init) {
+        CK(cudaMemcpyAsync(trcap, g->S.tr + node, sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+        CK(cudaStreamSynchronize(g->stream));
+        return MGC_OK;
+    }
+    double e = 0, s = 0;
+    CK(cudaMemcpyAsync(&e, g->S.excess + node, sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaMemcpyAsync(&s, g->S.sink + node, sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    *trcap = s > 0 ? -s : e;
+    return MGC_OK;
+}
+
+int mgc_get_node_num(const mgc_graph* g, int64_t* n)
+{
+    if (!g || !n) return MGC_E_ARG;
+    *n = (int64_t)g->L.n;
+    return MGC_OK;
+}
+
+int mgc_get_arc_num(const mgc_graph* g, int64_t* n)
+{
+    if (!g || !n) return MGC_E_ARG;
+    int64_t e = 0;
+    if (g->has_nlinks)
+        for (int d = 0; d < g->nd; ++d)
+            if (g->L.dim[d] > 1) e += ((int64_t)g->L.n / g->L.dim[d]) * (g->L.dim[d] - 1);
+    *n = 2 * e;
+    return MGC_OK;
+}
+
+int mgc_get_stats(const mgc_graph* g, mgc_stats* out)
+{
+    if (!g || !out) return MGC_E_ARG;
+    *out = g->st;
+    out->device_bytes = g->device_bytes;
+    return MGC_OK;
+}
+
+// ---- z-slab stepping --------------------------------------------------------------------------------
+
+int mgc_slab_plane_elems(const mgc_graph* g, int64_t* n)
+{
+    if (!g || !n) return MGC_E_ARG;
+    *n = (int64_t)g->L.plane;
+    return MGC_OK;
+}
+
+int mgc_slab_begin(mgc_graph* g)
+{
+    if (!g) return MGC_E_ARG;
+    CK(cudaSetDevice(g->device));
+    return ensure_state(g);
+}
+
+int mgc_slab_push(mgc_graph* g, int32_t n)
+{
+    if (!g || n < 0) return MGC_E_ARG;
+    if (!g->state_init) FAIL(MGC_E_STATE, "call mgc_slab_begin first");
+    CK(cudaSetDevice(g->device));
+    return push_sweeps(g, n, nullptr);
+}
+
+int mgc_slab_pack(mgc_graph* g, int32_t* h_lo, double* f_lo, int32_t* h_hi, double* f_hi)
+{
+    if (!g) return MGC_E_ARG;
+    CK(cudaSetDevice(g->device));
+    const unsigned P = g->L.plane;
+    const unsigned nb = (P + 255u) / 256u;
+    if (g->ghost_lo && h_lo && f_lo) {
+        const size_t border = (size_t)g->L.own0 * P, ghost = border - P;
+        k_slab_pack<double><<<nb, 256, 0, g->stream>>>(P, g->S.height + border, g->S.excess + ghost, h_lo, f_lo);
+        g->st.kernel_launches++;
+    }
+    if (g->ghost_hi && h_hi && f_hi) {
+        const size_t border = (size_t)(g->L.own1 - 1) * P, ghost = border + P;
+        k_slab_pack<double><<<nb, 256, 0, g->stream>>>(P, g->S.height + border, g->S.excess + ghost, h_hi, f_hi);
+        g->st.kernel_launches++;
+    }
+    CK(cudaGetLastError());
+    return MGC_OK;
+}
+
+int mgc_slab_unpack(mgc_graph* g, const int32_t* h_lo, const double* f_lo, const int32_t* h_hi, const double* f_hi)
+{
+    if (!g) return MGC_E_ARG;
+    CK(cudaSetDevice(g->device));
+    const unsigned P = g->L.plane;
+    const unsigned nb = (P + 255u) / 256u;
+    if (g->ghost_lo && h_lo && f_lo) {
+        const size_t border = (size_t)g->L.own0 * P, ghost = border - P;
+        // my arc border -> lower ghost is direction 0 (axis 0, -1)
+        k_slab_unpack<double><<<nb, 256, 0, g->stream>>>(P, g->S.height + ghost, g->S.excess + border, g->S.cap[0] + border, h_lo, f_lo, g->d_flags + 1);
+        g->st.kernel_launches++;
+    }
+    if (g->ghost_hi && h_hi && f_hi) {
+        const size_t border = (size_t)(g->L.own1 - 1) * P, ghost = border + P;
+        k_slab_unpack<double><<<nb, 256, 0, g->stream>>>(P, g->S.height + ghost, g->S.excess + border, g->S.cap[1] + border, h_hi, f_hi, g->d_flags + 1);
+        g->st.kernel_launches++;
+    }
+    CK(cudaGetLastError());
+    return MGC_OK;
+}
+
+int mgc_slab_relabel_begin(mgc_graph* g)
+{
+    if (!g) return MGC_E_ARG;
+    if (!g->state_init) FAIL(MGC_E_STATE, "call mgc_slab_begin first");
+    CK(cudaSetDevice(g->device));
+    g->st.global_relabels++;
+    return relabel_init(g);
+}
+
+int mgc_slab_relabel_relax(mgc_graph* g, int32_t* changed_out)
+{
+    if (!g || !changed_out) return MGC_E_ARG;
+    CK(cudaSetDevice(g->device));
+    // a ghost height changed by the preceding unpack counts as a change
+    int pre = 0;
+    CK(cudaMemcpyAsync(&pre, g->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    int any = 0;
+    int rc = relabel_relax(g, &any);
+    if (rc) return rc;
+    *changed_out = (any || pre) ? 1 : 0;
+    return MGC_OK;
+}
+
+int mgc_slab_count_active(mgc_graph* g, int64_t* active_out)
+{
+    if (!g || !active_out) return MGC_E_ARG;
+    CK(cudaSetDevice(g->device));
+    return count_active(g, active_out);
+}
+
+int mgc_slab_finish(mgc_graph* g, double* energy_part)
+{
+    if (!g || !energy_part) return MGC_E_ARG;
+    CK(cudaSetDevice(g->device));
+    int rc = readout(g, energy_part);
+    if (rc) return rc;
+    g->energy = *energy_part;
+    g->st.energy = g->energy;
+    g->solved = true;
+    return MGC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,61 @@
+// gc_common.cuh -- shared device-side types for the B200 voxel graph-cut path.
+//
+// Data layout in HBM (structure of arrays over the C-order flat voxel index v):
+//   cap[k][v]   residual capacity of the arc leaving v in direction k = 2*axis + (0: -1, 1: +1)
+//               (the implicit lattice replaces the reference's 48 B node / 32 B arc objects,
+//               lib/maxflow/src/graph.h:283-318); arcs that would leave the lattice hold 0 forever
+//   tr[v]       net terminal capacity exactly as Graph::add_tweights leaves it (graph.h:415-425)
+//   excess[v]   preflow excess;  sink[v] residual capacity v -> sink
+//   height[v]   push-relabel label (int32), HINF = cannot reach the sink
+//   rmask[v]    bit k set iff cap[k][v] > 0 (snapshot used by the global relabel)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define MGC_HINF 0x3fffffff
+#define MGC_MAXDIR 8
+
+struct Lattice {
+    int nd;                 // canonical number of axes: 3 or 4
+    int dim[4];             // extents, axis 0 slowest
+    unsigned stride[4];     // element strides (C order)
+    unsigned n;             // voxels in the local lattice (< 2^31)
+    unsigned plane;         // voxels per axis-0 plane
+    int own0, own1;         // owned axis-0 planes [own0, own1): all of them unless this is a z-slab
+};
+
+template <typename T>
+struct State {
+    T* cap[MGC_MAXDIR];
+    T* excess;
+    T* sink;
+    T* tr;
+    int* height;
+    uint8_t* rmask;
+};
+
+template <int ND>
+__device__ __forceinline__ void decode(const Lattice& L, unsigned v, int (&c)[ND])
+{
+    unsigned r = v;
+#pragma unroll
+    for (int d = 0; d < ND - 1; ++d) {
+        unsigned q = r / L.stride[d];
+        c[d] = (int)q;
+        r -= q * L.stride[d];
+    }
+    c[ND - 1] = (int)r;
+}
+
+// signed element offset of direction k
+__device__ __forceinline__ int dir_offset(const Lattice& L, int k)
+{
+    int s = (int)L.stride[k >> 1];
+    return (k & 1) ? s : -s;
+}
+
+__device__ __forceinline__ bool owned(const Lattice& L, unsigned v)
+{
+    int p = (int)(v / L.plane);
+    return p >= L.own0 && p < L.own1;
+}

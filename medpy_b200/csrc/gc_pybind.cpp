@@ -1,0 +1,269 @@
+// gc_pybind.cpp -- thin pybind11 module `medpy_b200._mgc` over the C ABI (include/medpy_b200_graphcut.h).
+//
+// It plays the role of the reference's Boost.Python module `medpy.graphcut.maxflow`
+// (lib/maxflow/src/wrapper.cpp:59-89,125-134): one Python class owning one native graph.  Unlike the
+// reference binding, whole arrays cross the boundary (numpy buffers or anything exposing
+// __cuda_array_interface__, e.g. torch CUDA tensors) and the GIL is released around every native call.
+// No arithmetic lives here.
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <cmath>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/medpy_b200_graphcut.h"
+
+namespace py = pybind11;
+
+namespace {
+
+void check(int rc, const mgc_graph* g)
+{
+    if (rc == MGC_OK) return;
+    std::string msg = mgc_last_error(g);
+    if (msg.empty()) msg = "medpy_b200 graph-cut error " + std::to_string(rc);
+    if (rc == MGC_E_ARG || rc == MGC_E_WEIGHT) throw py::value_error(msg);
+    throw std::runtime_error(msg);
+}
+
+int dtype_code(const std::string& kind_size)
+{
+    if (kind_size == "f4") return MGC_F32;
+    if (kind_size == "f8") return MGC_F64;
+    if (kind_size == "u1" || kind_size == "b1") return MGC_U8;
+    if (kind_size == "i2") return MGC_I16;
+    if (kind_size == "i4") return MGC_I32;
+    return -1;
+}
+
+// Holds the mgc_array plus whatever keeps the memory alive for the duration of the call.
+struct ArrayRef {
+    mgc_array a{};
+    py::object keep;
+    std::vector<int64_t> shape;
+};
+
+ArrayRef make_ref(const py::object& obj, int want_dtype /* -1 any */, const char* what)
+{
+    ArrayRef r;
+    if (py::hasattr(obj, "__cuda_array_interface__")) {
+        py::dict d = obj.attr("__cuda_array_interface__");
+        py::tuple data = d["data"];
+        r.a.data = reinterpret_cast<const void*>(data[0].cast<uintptr_t>());
+        r.a.mem = MGC_MEM_DEVICE;
+        std::string ts = d["typestr"].cast<std::string>();  // e.g. "<f4", "|u1", "|b1"
+        r.a.dtype = dtype_code(ts.substr(1));
+        py::tuple shp = d["shape"];
+        for (auto s : shp) r.shape.push_back(s.cast<int64_t>());
+        size_t es = (size_t)std::stoi(ts.substr(2));
+        if (d.contains("strides") && !d["strides"].is_none()) {
+            py::tuple st = d["strides"];
+            for (size_t i = 0; i < st.size() && i < MGC_MAX_NDIM; ++i) r.a.strides[i] = st[i].cast<int64_t>();
+        } else {
+            int64_t acc = (int64_t)es;
+            for (int i = (int)r.shape.size() - 1; i >= 0; --i) { if (i < MGC_MAX_NDIM) r.a.strides[i] = acc; acc *= r.shape[i]; }
+        }
+        r.keep = obj;
+    } else {
+        py::array arr = py::array::ensure(obj);
+        if (!arr) throw py::value_error(std::string(what) + ": expected an array");
+        std::string ks(1, arr.dtype().kind());
+        ks += std::to_string(arr.dtype().itemsize());
+        r.a.dtype = dtype_code(ks);
+        r.a.data = arr.data();
+        r.a.mem = MGC_MEM_HOST;
+        for (py::ssize_t i = 0; i < arr.ndim(); ++i) {
+            r.shape.push_back(arr.shape(i));
+            if (i < MGC_MAX_NDIM) r.a.strides[i] = arr.strides(i);
+        }
+        r.keep = arr;
+    }
+    if (r.a.dtype < 0) throw py::value_error(std::string(what) + ": unsupported dtype");
+    if (want_dtype >= 0 && r.a.dtype != want_dtype) throw py::value_error(std::string(what) + ": wrong dtype");
+    return r;
+}
+
+class PyGraph {
+public:
+    PyGraph(const std::vector<int64_t>& shape, int device) : shape_(shape)
+    {
+        int rc = mgc_create((int32_t)shape.size(), shape.data(), device, &g_);
+        if (rc != MGC_OK) { std::string m = mgc_last_error(nullptr); if (rc == MGC_E_ARG) throw py::value_error(m); throw std::runtime_error(m); }
+    }
+    PyGraph(const std::vector<int64_t>& shape, int64_t z0, int64_t z1, int device) : shape_(shape)
+    {
+        int rc = mgc_create_slab((int32_t)shape.size(), shape.data(), z0, z1, device, &g_);
+        if (rc != MGC_OK) { std::string m = mgc_last_error(nullptr); if (rc == MGC_E_ARG) throw py::value_error(m); throw std::runtime_error(m); }
+        shape_[0] = (z1 - z0) + (z0 > 0 ? 1 : 0) + (z1 < shape[0] ? 1 : 0);  // local extent incl. ghost planes
+        owned_planes_ = z1 - z0;
+    }
+    ~PyGraph() { if (g_) mgc_destroy(g_); }
+    PyGraph(const PyGraph&) = delete;
+    PyGraph& operator=(const PyGraph&) = delete;
+
+    void check_shape(const ArrayRef& r, const char* what) const
+    {
+        if (r.shape != shape_) throw py::value_error(std::string(what) + ": shape does not match the graph's lattice");
+    }
+
+    void add_regional_probability(const py::object& prob, double alpha, bool compute_f32)
+    {
+        ArrayRef r = make_ref(prob, -1, "probability_map");
+        check_shape(r, "probability_map");
+        int rc;
+        { py::gil_scoped_release rel; rc = mgc_add_regional_probability(g_, &r.a, alpha, compute_f32 ? MGC_F32 : MGC_F64); }
+        check(rc, g_);
+    }
+    void add_tweights_dense(const py::object& src, const py::object& snk)
+    {
+        ArrayRef a = make_ref(src, MGC_F64, "src"), b = make_ref(snk, MGC_F64, "snk");
+        check_shape(a, "src"); check_shape(b, "snk");
+        int rc;
+        { py::gil_scoped_release rel; rc = mgc_add_tweights_dense(g_, &a.a, &b.a); }
+        check(rc, g_);
+    }
+    void add_markers(const py::object& fg, const py::object& bg)
+    {
+        ArrayRef a, b;
+        bool hf = !fg.is_none(), hb = !bg.is_none();
+        if (hf) { a = make_ref(fg, MGC_U8, "fg_markers"); check_shape(a, "fg_markers"); }
+        if (hb) { b = make_ref(bg, MGC_U8, "bg_markers"); check_shape(b, "bg_markers"); }
+        int rc;
+        { py::gil_scoped_release rel; rc = mgc_add_markers(g_, hf ? &a.a : nullptr, hb ? &b.a : nullptr); }
+        check(rc, g_);
+    }
+    void add_boundary(int kind, const py::object& image, double sigma, const py::object& spacing, double norm)
+    {
+        ArrayRef r = make_ref(image, -1, "image");
+        check_shape(r, "image");
+        std::vector<double> sp;
+        if (!spacing.is_none()) {
+            sp = spacing.cast<std::vector<double>>();
+            if (sp.size() < shape_.size()) throw py::value_error("spacing has fewer entries than the image has dimensions");
+        }
+        int rc;
+        { py::gil_scoped_release rel; rc = mgc_add_boundary(g_, kind, &r.a, sigma, sp.empty() ? nullptr : sp.data(), norm); }
+        check(rc, g_);
+    }
+    void add_nweights_dense(int axis, const py::object& fwd, const py::object& bwd)
+    {
+        ArrayRef a = make_ref(fwd, MGC_F64, "fwd"), b = make_ref(bwd, MGC_F64, "bwd");
+        check_shape(a, "fwd"); check_shape(b, "bwd");
+        int rc;
+        { py::gil_scoped_release rel; rc = mgc_add_nweights_dense(g_, axis, &a.a, &b.a); }
+        check(rc, g_);
+    }
+    double maxflow()
+    {
+        double e = 0;
+        int rc;
+        { py::gil_scoped_release rel; rc = mgc_maxflow(g_, &e); }
+        check(rc, g_);
+        return e;
+    }
+    py::array_t<uint8_t> get_mask()
+    {
+        std::vector<py::ssize_t> shp(shape_.begin(), shape_.end());
+        if (owned_planes_ >= 0) shp[0] = owned_planes_;
+        py::array_t<uint8_t> out(shp);
+        int rc;
+        { uint8_t* p = out.mutable_data(); py::gil_scoped_release rel; rc = mgc_get_mask(g_, p, MGC_MEM_HOST); }
+        check(rc, g_);
+        return out;
+    }
+    void get_mask_into(uintptr_t device_ptr)
+    {
+        int rc;
+        { py::gil_scoped_release rel; rc = mgc_get_mask(g_, reinterpret_cast<uint8_t*>(device_ptr), MGC_MEM_DEVICE); }
+        check(rc, g_);
+    }
+    int what_segment(int64_t i) { int32_t s = 0; check(mgc_what_segment(g_, i, &s), g_); return s; }
+    double get_edge(int64_t i, int64_t j) { double c = 0; check(mgc_get_edge(g_, i, j, &c), g_); return c; }
+    double get_trcap(int64_t i) { double c = 0; check(mgc_get_trcap(g_, i, &c), g_); return c; }
+    int64_t get_node_num() { int64_t n = 0; check(mgc_get_node_num(g_, &n), g_); return n; }
+    int64_t get_arc_num() { int64_t n = 0; check(mgc_get_arc_num(g_, &n), g_); return n; }
+    void reset() { check(mgc_reset(g_), g_); }
+    void set_stream(uintptr_t s) { check(mgc_set_stream(g_, reinterpret_cast<void*>(s)), g_); }
+    void synchronize() { int rc; { py::gil_scoped_release rel; rc = mgc_synchronize(g_); } check(rc, g_); }
+    py::dict stats()
+    {
+        mgc_stats s{};
+        check(mgc_get_stats(g_, &s), g_);
+        py::dict d;
+        d["n_voxels"] = s.n_voxels; d["push_sweeps"] = s.push_sweeps; d["global_relabels"] = s.global_relabels;
+        d["relabel_sweeps"] = s.relabel_sweeps; d["kernel_launches"] = s.kernel_launches; d["active_last"] = s.active_last;
+        d["ms_terms"] = s.ms_terms; d["ms_solve"] = s.ms_solve; d["ms_readout"] = s.ms_readout;
+        d["flow_const"] = s.flow_const; d["energy"] = s.energy; d["device_bytes"] = s.device_bytes;
+        return d;
+    }
+    // ---- z-slab stepping (device pointers as integers, e.g. torch.Tensor.data_ptr()) ----
+    int64_t slab_plane_elems() { int64_t n = 0; check(mgc_slab_plane_elems(g_, &n), g_); return n; }
+    void slab_begin() { int rc; { py::gil_scoped_release rel; rc = mgc_slab_begin(g_); } check(rc, g_); }
+    void slab_push(int n) { int rc; { py::gil_scoped_release rel; rc = mgc_slab_push(g_, n); } check(rc, g_); }
+    void slab_pack(uintptr_t hlo, uintptr_t flo, uintptr_t hhi, uintptr_t fhi)
+    {
+        int rc;
+        { py::gil_scoped_release rel; rc = mgc_slab_pack(g_, (int32_t*)hlo, (double*)flo, (int32_t*)hhi, (double*)fhi); }
+        check(rc, g_);
+    }
+    void slab_unpack(uintptr_t hlo, uintptr_t flo, uintptr_t hhi, uintptr_t fhi)
+    {
+        int rc;
+        { py::gil_scoped_release rel; rc = mgc_slab_unpack(g_, (const int32_t*)hlo, (const double*)flo, (const int32_t*)hhi, (const double*)fhi); }
+        check(rc, g_);
+    }
+    void slab_relabel_begin() { int rc; { py::gil_scoped_release rel; rc = mgc_slab_relabel_begin(g_); } check(rc, g_); }
+    int slab_relabel_relax() { int32_t c = 0; int rc; { py::gil_scoped_release rel; rc = mgc_slab_relabel_relax(g_, &c); } check(rc, g_); return c; }
+    int64_t slab_count_active() { int64_t a = 0; int rc; { py::gil_scoped_release rel; rc = mgc_slab_count_active(g_, &a); } check(rc, g_); return a; }
+    double slab_finish() { double e = 0; int rc; { py::gil_scoped_release rel; rc = mgc_slab_finish(g_, &e); } check(rc, g_); return e; }
+
+    std::vector<int64_t> shape() const { return shape_; }
+
+private:
+    mgc_graph* g_ = nullptr;
+    std::vector<int64_t> shape_;
+    int64_t owned_planes_ = -1;
+};
+
+}  // namespace
+
+PYBIND11_MODULE(_mgc, m)
+{
+    m.doc() = "pybind11 binding of libmedpy_b200_gc (B200 voxel graph-cut C ABI)";
+    m.attr("ABI_VERSION") = mgc_abi_version();
+    m.attr("SOURCE") = MGC_SOURCE;
+    m.attr("SINK") = MGC_SINK;
+    py::class_<PyGraph>(m, "Graph")
+        .def(py::init<const std::vector<int64_t>&, int>(), py::arg("shape"), py::arg("device") = -1)
+        .def(py::init<const std::vector<int64_t>&, int64_t, int64_t, int>(), py::arg("shape"), py::arg("z0"), py::arg("z1"), py::arg("device") = -1)
+        .def("add_regional_probability", &PyGraph::add_regional_probability)
+        .def("add_tweights_dense", &PyGraph::add_tweights_dense)
+        .def("add_markers", &PyGraph::add_markers)
+        .def("add_boundary", &PyGraph::add_boundary)
+        .def("add_nweights_dense", &PyGraph::add_nweights_dense)
+        .def("maxflow", &PyGraph::maxflow)
+        .def("get_mask", &PyGraph::get_mask)
+        .def("get_mask_into", &PyGraph::get_mask_into)
+        .def("what_segment", &PyGraph::what_segment)
+        .def("get_edge", &PyGraph::get_edge)
+        .def("get_trcap", &PyGraph::get_trcap)
+        .def("get_node_num", &PyGraph::get_node_num)
+        .def("get_arc_num", &PyGraph::get_arc_num)
+        .def("reset", &PyGraph::reset)
+        .def("set_stream", &PyGraph::set_stream)
+        .def("synchronize", &PyGraph::synchronize)
+        .def("stats", &PyGraph::stats)
+        .def("slab_plane_elems", &PyGraph::slab_plane_elems)
+        .def("slab_begin", &PyGraph::slab_begin)
+        .def("slab_push", &PyGraph::slab_push)
+        .def("slab_pack", &PyGraph::slab_pack)
+        .def("slab_unpack", &PyGraph::slab_unpack)
+        .def("slab_relabel_begin", &PyGraph::slab_relabel_begin)
+        .def("slab_relabel_relax", &PyGraph::slab_relabel_relax)
+        .def("slab_count_active", &PyGraph::slab_count_active)
+        .def("slab_finish", &PyGraph::slab_finish)
+        .def_property_readonly("shape", &PyGraph::shape);
+}

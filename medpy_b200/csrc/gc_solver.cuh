@@ -1,0 +1,212 @@
+// gc_solver.cuh -- lattice push-relabel max-flow kernels (replace Graph::maxflow, maxflow.cpp:471-604).
+//
+// Algorithm: maximum PREFLOW by lock-free push-relabel on the implicit lattice, with an
+// exact backward BFS from the sink (global relabel) every few sweeps.  The min cut the reference reports
+// is solver independent: what_segment(v) == SINK  <=>  v can still reach the sink in the residual graph
+// (SURVEY.md §3.3), which is exactly "height[v] finite after an exact global relabel" of a maximum
+// preflow.  The stop test is only ever made right after such a relabel: no voxel with excess > 0 has a
+// finite label.
+#pragma once
+#include "gc_common.cuh"
+
+// ---------------------------------------------------------------------------------------------------
+// init: excess = min(max(tr,0), roundup(sum of out-capacities)), sink = max(-tr,0)
+// Clamping the source link to what can leave the voxel changes neither the cut value nor the minimal
+// sink set, and keeps the 65535 hard-marker links from flooding the lattice.
+// ---------------------------------------------------------------------------------------------------
+template <int ND, typename T>
+__global__ void __launch_bounds__(256) k_init_state(Lattice L, State<T> S)
+{
+    unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= L.n) return;
+    double tr = (double)S.tr[v];
+    double e = 0.0, s = 0.0;
+    if (tr > 0) {
+        double out = 0.0;
+#pragma unroll
+        for (int k = 0; k < 2 * ND; ++k) out = __dadd_ru(out, (double)S.cap[k][v]);
+        e = tr < out ? tr : out;
+        if (!(out == out)) e = tr;  // NaN capacities (zero-image linear terms): leave the link alone
+    } else if (tr < 0) {
+        s = -tr;
+    }
+    if (!owned(L, v)) e = 0.0;      // ghost planes of a z-slab start with an empty outbox
+    S.excess[v] = (T)e;
+    S.sink[v] = (T)s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// push / relabel sweep: one thread per voxel, lock-free (Hong & He style): an active voxel pushes to its
+// lowest residual neighbours while they are strictly lower, then relabels to 1 + the lowest remaining
+// residual neighbour.  Neighbour state is updated with atomics; own excess is corrected by an atomic
+// subtraction because neighbours add to it concurrently.  `work` is set when anything was active.
+// ---------------------------------------------------------------------------------------------------
+template <int ND, typename T>
+__global__ void __launch_bounds__(256) k_push(Lattice L, State<T> S, int* __restrict__ work)
+{
+    unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= L.n) return;
+    T e = S.excess[v];
+    if (!(e > 0)) return;
+    int h = S.height[v];
+    if (h >= MGC_HINF) return;
+    if (!owned(L, v)) return;
+    *work = 1;
+    T pushed = 0;
+    T s = S.sink[v];
+    if (s > 0) {                      // the sink sits at height 0: always admissible
+        T d = e < s ? e : s;
+        S.sink[v] = s - d;
+        e -= d;
+        pushed += d;
+    }
+    if (e > 0) {
+        T c[2 * ND];
+        int hn[2 * ND];
+#pragma unroll
+        for (int k = 0; k < 2 * ND; ++k) {
+            c[k] = S.cap[k][v];
+            hn[k] = MGC_HINF;
+            if (c[k] > 0) hn[k] = S.height[(int)v + dir_offset(L, k)];
+        }
+        int newh = h;
+#pragma unroll 1
+        for (int it = 0; it < 2 * ND; ++it) {
+            int kb = -1, hb = MGC_HINF;
+#pragma unroll
+            for (int k = 0; k < 2 * ND; ++k)
+                if (c[k] > 0 && hn[k] < hb) { hb = hn[k]; kb = k; }
+            if (kb < 0) { newh = MGC_HINF; break; }          // no residual arc left: can never reach the sink
+            if (hb >= h) { newh = hb + 1; break; }            // relabel
+            T d = e < c[kb] ? e : c[kb];
+            unsigned w = (unsigned)((int)v + dir_offset(L, kb));
+            atomicAdd(&S.cap[kb][v], -d);
+            atomicAdd(&S.cap[kb ^ 1][w], d);
+            atomicAdd(&S.excess[w], d);
+            e -= d;
+            pushed += d;
+            c[kb] = 0;                                        // saturated, or e is exhausted
+            if (!(e > 0)) break;
+        }
+        if (newh != h) S.height[v] = newh;
+    }
+    if (pushed > 0) atomicAdd(&S.excess[v], -pushed);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// global relabel: exact distances to the sink in the residual graph by in-place relaxation
+// ---------------------------------------------------------------------------------------------------
+template <int ND, typename T>
+__global__ void __launch_bounds__(256) k_relabel_init(Lattice L, State<T> S)
+{
+    unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= L.n) return;
+    unsigned m = 0;
+#pragma unroll
+    for (int k = 0; k < 2 * ND; ++k)
+        if (S.cap[k][v] > 0) m |= 1u << k;
+    S.rmask[v] = (uint8_t)m;
+    // ghost planes restart at HINF: a from-scratch BFS must only ever see upper bounds, otherwise two slabs
+    // can keep each other's stale finite labels alive (count-to-infinity) and the stop test never fires
+    S.height[v] = (owned(L, v) && S.sink[v] > 0) ? 1 : MGC_HINF;
+}
+
+template <int ND>
+__global__ void __launch_bounds__(256) k_relabel_relax(Lattice L, const uint8_t* __restrict__ rmask,
+                                                        int* __restrict__ height, int* __restrict__ changed)
+{
+    unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= L.n) return;
+    unsigned m = rmask[v];
+    if (!m) return;
+    if (!owned(L, v)) return;
+    int h = height[v];
+    if (h <= 1) return;
+    int best = h;
+#pragma unroll
+    for (int k = 0; k < 2 * ND; ++k) {
+        if (m & (1u << k)) {
+            int hw = height[(int)v + dir_offset(L, k)] + 1;
+            best = hw < best ? hw : best;
+        }
+    }
+    if (best < h) {
+        height[v] = best;
+        *changed = 1;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_count_active(Lattice L, State<T> S, unsigned long long* __restrict__ count)
+{
+    unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    bool act = false;
+    if (v < L.n) act = (S.excess[v] > 0) && (S.height[v] < MGC_HINF) && owned(L, v);
+    unsigned b = __ballot_sync(0xffffffffu, act);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, (unsigned long long)__popc(b));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// read-out: mask (K5) and energy (K6)
+// ---------------------------------------------------------------------------------------------------
+// mask[v] = 1 unless v can reach the sink (bin/medpy_graphcut_voxel.py:177-181 with graph.h:560-571)
+__global__ void __launch_bounds__(256) k_mask(Lattice L, const int* __restrict__ height, uint8_t* __restrict__ mask)
+{
+    unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= L.n) return;
+    mask[v] = height[v] >= MGC_HINF ? 1 : 0;
+}
+
+// flow absorbed by the sink links of the owned voxels: sum(max(-tr,0) - sink_residual); deterministic
+template <typename T>
+__global__ void __launch_bounds__(256) k_absorbed(Lattice L, State<T> S, double* __restrict__ partials)
+{
+    __shared__ double sh[256];
+    unsigned tid = threadIdx.x;
+    unsigned v = blockIdx.x * blockDim.x + tid;
+    double a = 0.0;
+    if (v < L.n && owned(L, v)) {
+        double tr = (double)S.tr[v];
+        if (tr < 0) a = __dsub_rn(-tr, (double)S.sink[v]);
+    }
+    sh[tid] = a;
+    __syncthreads();
+    for (unsigned s = 128; s > 0; s >>= 1) {
+        if (tid < s) sh[tid] = __dadd_rn(sh[tid], sh[tid + s]);
+        __syncthreads();
+    }
+    if (tid == 0) partials[blockIdx.x] = sh[0];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// z-slab border messages
+// ---------------------------------------------------------------------------------------------------
+// pack: heights of my border plane + the flow parked in the ghost plane's excess (my outbox), which is cleared
+template <typename T>
+__global__ void k_slab_pack(unsigned plane, const int* __restrict__ height_border, T* __restrict__ excess_ghost,
+                            int* __restrict__ h_out, double* __restrict__ f_out)
+{
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= plane) return;
+    h_out[i] = height_border[i];
+    f_out[i] = (double)excess_ghost[i];
+    excess_ghost[i] = 0;
+}
+
+// unpack: ghost heights <- neighbour's border heights; received flow joins the excess of my border voxel
+// and the residual of my arc towards the ghost (it is the reverse of the arc the flow arrived on)
+template <typename T>
+__global__ void k_slab_unpack(unsigned plane, int* __restrict__ height_ghost, T* __restrict__ excess_border,
+                              T* __restrict__ cap_border_to_ghost, const int* __restrict__ h_in,
+                              const double* __restrict__ f_in, int* __restrict__ changed)
+{
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= plane) return;
+    int hn = h_in[i];
+    if (height_ghost[i] != hn) { height_ghost[i] = hn; *changed = 1; }
+    double f = f_in[i];
+    if (f > 0) {
+        excess_border[i] += (T)f;
+        cap_border_to_ghost[i] += (T)f;
+    }
+}

@@ -1,0 +1,295 @@
+// gc_terms.cuh -- energy-term kernels: K0 (min/max), K1 (n-link stencils), K2 (t-links / markers).
+//
+// They replace the reference's per-edge / per-node Python loops
+//   energy_voxel.py:611-664 (__skeleton_base) -> GCGraph.set_nweight -> Graph::sum_edge (graph.h:456-480)
+//   graph.py:532-552 (set_tweights_all), :310-380 (set_source_nodes/set_sink_nodes)
+//     -> Graph::add_tweights (graph.h:415-425)
+// All arithmetic is float64 with explicitly rounded operations (no FMA contraction) so the weights
+// equal numpy's bit for bit wherever numpy's own operations are correctly rounded (+,-,*,/); exp and
+// pow are within an ulp or two of numpy's libm.
+#pragma once
+#include "gc_common.cuh"
+#include <cfloat>
+
+// ---------------------------------------------------------------------------------------------------
+// input element access
+// ---------------------------------------------------------------------------------------------------
+template <typename E> struct Elem;
+template <> struct Elem<float> {
+    static __device__ __forceinline__ double val(float x) { return (double)x; }
+    static __device__ __forceinline__ float absv(float x) { return fabsf(x); }
+};
+template <> struct Elem<double> {
+    static __device__ __forceinline__ double val(double x) { return x; }
+    static __device__ __forceinline__ double absv(double x) { return fabs(x); }
+};
+template <> struct Elem<uint8_t> {
+    static __device__ __forceinline__ double val(uint8_t x) { return (double)x; }
+    static __device__ __forceinline__ uint8_t absv(uint8_t x) { return x; }
+};
+template <> struct Elem<int16_t> {
+    static __device__ __forceinline__ double val(int16_t x) { return (double)x; }
+    // numpy.abs on int16 wraps for -32768 (energy_voxel.py:558 works in the input dtype)
+    static __device__ __forceinline__ int16_t absv(int16_t x) { return (int16_t)(x < 0 ? -x : x); }
+};
+template <> struct Elem<int32_t> {
+    static __device__ __forceinline__ double val(int32_t x) { return (double)x; }
+    static __device__ __forceinline__ int32_t absv(int32_t x) { return (int32_t)(x < 0 ? (int32_t)(0u - (unsigned)x) : x); }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// strided gather: arbitrary positive byte strides -> C-contiguous (used for Fortran-ordered inputs
+// such as medpy.io.load returns, io/load.py:125-127)
+// ---------------------------------------------------------------------------------------------------
+struct Strides4 { long long s[4]; };
+
+template <typename E, int ND>
+__global__ void k_gather(Lattice L, const char* __restrict__ src, Strides4 st, E* __restrict__ dst)
+{
+    unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= L.n) return;
+    int c[ND];
+    decode<ND>(L, v, c);
+    long long off = 0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) off += (long long)c[d] * st.s[d];
+    dst[v] = *reinterpret_cast<const E*>(src + off);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K0: global min / max (difference_linear: |max - min| in the input dtype, energy_voxel.py:174;
+//     maximum_linear: max |x| in the input dtype, energy_voxel.py:99)
+// ---------------------------------------------------------------------------------------------------
+template <typename E>
+__global__ void k_minmax_partial(const E* __restrict__ img, unsigned n, E* __restrict__ pmin, E* __restrict__ pmax,
+                                 E* __restrict__ pabs)
+{
+    __shared__ E smin[256], smax[256], sabs[256];
+    unsigned tid = threadIdx.x;
+    unsigned i = blockIdx.x * blockDim.x + tid;
+    unsigned step = gridDim.x * blockDim.x;
+    E lo = img[0], hi = img[0], ab = Elem<E>::absv(img[0]);
+    for (; i < n; i += step) {
+        E x = img[i];
+        E a = Elem<E>::absv(x);
+        lo = x < lo ? x : lo;
+        hi = x > hi ? x : hi;
+        ab = a > ab ? a : ab;
+    }
+    smin[tid] = lo; smax[tid] = hi; sabs[tid] = ab;
+    __syncthreads();
+    for (unsigned s = 128; s > 0; s >>= 1) {
+        if (tid < s) {
+            smin[tid] = smin[tid + s] < smin[tid] ? smin[tid + s] : smin[tid];
+            smax[tid] = smax[tid + s] > smax[tid] ? smax[tid + s] : smax[tid];
+            sabs[tid] = sabs[tid + s] > sabs[tid] ? sabs[tid + s] : sabs[tid];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { pmin[blockIdx.x] = smin[0]; pmax[blockIdx.x] = smax[0]; pabs[blockIdx.x] = sabs[0]; }
+}
+
+// out[0] = float(abs(max - min)) computed in E; out[1] = float(max |x|)
+template <typename E>
+__global__ void k_minmax_final(const E* pmin, const E* pmax, const E* pabs, unsigned nb, double* out)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    E lo = pmin[0], hi = pmax[0], ab = pabs[0];
+    for (unsigned i = 1; i < nb; ++i) {
+        lo = pmin[i] < lo ? pmin[i] : lo;
+        hi = pmax[i] > hi ? pmax[i] : hi;
+        ab = pabs[i] > ab ? pabs[i] : ab;
+    }
+    E diff = (E)(hi - lo);            // in the input dtype, like numpy (wraps for narrow ints)
+    diff = Elem<E>::absv(diff);
+    out[0] = Elem<E>::val(diff);
+    out[1] = Elem<E>::val(ab);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1: boundary (n-link) stencil
+// ---------------------------------------------------------------------------------------------------
+struct BoundaryParams {
+    int fn;            // 0 linear, 1 exponential, 2 division, 3 power
+    int use_max;       // 1: g(max(|a|,|b|)) (energy_voxel.py:519-558), 0: g(|a-b|) (:561-608)
+    double norm;       // linear: M
+    double sigma;      // division / power: sigma ; exponential: pow(sigma, 2)
+    double inv_spacing_on; // 0: no spacing
+    double spacing[4]; // canonical axes
+};
+
+__device__ __forceinline__ double g_weight(const BoundaryParams& P, double x)
+{
+    double w;
+    if (P.fn == 0) {                       // energy_voxel.py:101-114,176-189
+        w = __dsub_rn(1.0, __ddiv_rn(x, P.norm));
+        if (w == 0.0) w = DBL_MIN;
+    } else if (P.fn == 1) {                // :226-236,290-300
+        double t = __ddiv_rn(__dmul_rn(x, x), P.sigma);
+        w = exp(-t);
+        if (w <= 0.0) w = DBL_MIN;
+    } else if (P.fn == 2) {                // :337-345,399-407
+        w = __ddiv_rn(1.0, __dadd_rn(__ddiv_rn(x, P.sigma), 1.0));
+        if (w <= 0.0) w = DBL_MIN;
+    } else {                               // :444-452,506-514
+        w = pow(__ddiv_rn(1.0, __dadd_rn(x, 1.0)), P.sigma);
+        if (w <= 0.0) w = DBL_MIN;
+    }
+    return w;
+}
+
+// One thread per voxel p: for every axis d with p_d < D_d-1 computes the weight of the pair (p, q=p+e_d) once
+// and adds it to cap(p->q) [array 2d+1, index p] and cap(q->p) [array 2d, index q]; both stores are
+// coalesced because q = p + stride_d is contiguous in p.  `bad` is set if a weight <= 0 appears
+// (GCGraph.set_nweight raises ValueError there, graph.py:436-437; NaN passes, like the reference).
+template <typename E, int ND, typename T>
+__global__ void __launch_bounds__(256)
+k_boundary(Lattice L, State<T> S, const E* __restrict__ img, BoundaryParams P, int* __restrict__ bad)
+{
+    unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= L.n) return;
+    int c[ND];
+    decode<ND>(L, p, c);
+    E ip = img[p];
+    double a = P.use_max ? Elem<E>::val(Elem<E>::absv(ip)) : Elem<E>::val(ip);
+    int isbad = 0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        if (c[d] + 1 < L.dim[d]) {
+            unsigned q = p + L.stride[d];
+            E iq = img[q];
+            double b = P.use_max ? Elem<E>::val(Elem<E>::absv(iq)) : Elem<E>::val(iq);
+            double x = P.use_max ? fmax(a, b) : fabs(__dsub_rn(a, b));
+            double w = g_weight(P, x);
+            if (P.inv_spacing_on != 0.0) w = __ddiv_rn(w, P.spacing[d]);
+            if (w <= 0.0) isbad = 1;
+            S.cap[2 * d + 1][p] += (T)w;
+            S.cap[2 * d][q] += (T)w;
+        }
+    }
+    if (isbad) *bad = 1;
+}
+
+// dense user-supplied n-links along one axis (sum_edge semantics)
+template <int ND, typename T>
+__global__ void k_nweights_dense(Lattice L, State<T> S, int axis, const double* __restrict__ fwd,
+                                 const double* __restrict__ bwd, int* __restrict__ bad)
+{
+    unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= L.n) return;
+    int c[ND];
+    decode<ND>(L, p, c);
+    if (c[axis] + 1 >= L.dim[axis]) return;
+    double f = fwd[p], b = bwd[p];
+    if (f < 0.0 || b < 0.0) *bad = 1;   // Graph::sum_edge asserts cap >= 0 (graph.h:462-463); 0 = pair not set
+    S.cap[2 * axis + 1][p] += (T)f;
+    S.cap[2 * axis][p + L.stride[axis]] += (T)b;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2: t-links.  add_tweights (graph.h:415-425):
+//     delta = tr; if (delta > 0) s += delta; else t -= delta; flow += min(s,t); tr = s - t
+// The flow constant is reduced deterministically: per-block tree -> partials -> k_sum_partials.
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ double add_tweights_dev(T& tr, double s, double t)
+{
+    double delta = (double)tr;
+    if (delta > 0) s = __dadd_rn(s, delta); else t = __dsub_rn(t, delta);
+    tr = (T)__dsub_rn(s, t);
+    return (s < t) ? s : t;
+}
+
+__device__ __forceinline__ void block_sum_store(double x, double* __restrict__ partials)
+{
+    __shared__ double sh[256];
+    unsigned tid = threadIdx.x;
+    sh[tid] = x;
+    __syncthreads();
+    for (unsigned s = 128; s > 0; s >>= 1) {
+        if (tid < s) sh[tid] = __dadd_rn(sh[tid], sh[tid + s]);
+        __syncthreads();
+    }
+    if (tid == 0) partials[blockIdx.x] = sh[0];
+}
+
+// regional_probability_map (energy_voxel.py:62-65): products formed in the map's dtype when F32 != 0
+template <typename E, typename T>
+__global__ void __launch_bounds__(256)
+k_regional(Lattice L, State<T> S, const E* __restrict__ prob, double alpha, int compute_f32, double* __restrict__ partials)
+{
+    unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    double m = 0.0;
+    if (v < L.n) {
+        double s, t;
+        if (compute_f32) {
+            float p = (float)prob[v];
+            float a = (float)alpha;
+            s = (double)__fmul_rn(p, a);
+            t = (double)__fmul_rn(__fsub_rn(1.0f, p), a);
+        } else {
+            double p = (double)prob[v];
+            s = __dmul_rn(p, alpha);
+            t = __dmul_rn(__dsub_rn(1.0, p), alpha);
+        }
+        T tr = S.tr[v];
+        double mm = add_tweights_dev(tr, s, t);
+        S.tr[v] = tr;
+        if (owned(L, v)) m = mm;
+    }
+    block_sum_store(m, partials);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_tweights_dense(Lattice L, State<T> S, const double* __restrict__ src, const double* __restrict__ snk,
+                 double* __restrict__ partials)
+{
+    unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    double m = 0.0;
+    if (v < L.n) {
+        T tr = S.tr[v];
+        double mm = add_tweights_dev(tr, src[v], snk[v]);
+        S.tr[v] = tr;
+        if (owned(L, v)) m = mm;
+    }
+    block_sum_store(m, partials);
+}
+
+// set_source_nodes then set_sink_nodes (generate.py:169-172; MAX = 65535, graph.py:286-291)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_markers(Lattice L, State<T> S, const uint8_t* __restrict__ fg, const uint8_t* __restrict__ bg,
+          double* __restrict__ partials)
+{
+    unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    double m = 0.0;
+    if (v < L.n) {
+        bool f = fg && fg[v], b = bg && bg[v];
+        if (f || b) {
+            T tr = S.tr[v];
+            double mm = 0.0;
+            if (f) mm = add_tweights_dev(tr, 65535.0, 0.0);
+            if (b) mm = __dadd_rn(mm, add_tweights_dev(tr, 0.0, 65535.0));
+            S.tr[v] = tr;
+            if (owned(L, v)) m = mm;
+        }
+    }
+    block_sum_store(m, partials);
+}
+
+// acc[0] += sum(partials[0..n)) in a fixed order: 256 interleaved chains + tree (deterministic)
+__global__ void k_sum_partials(const double* __restrict__ partials, unsigned n, double* __restrict__ acc)
+{
+    __shared__ double sh[256];
+    unsigned tid = threadIdx.x;
+    double s = 0.0;
+    for (unsigned i = tid; i < n; i += 256) s = __dadd_rn(s, partials[i]);
+    sh[tid] = s;
+    __syncthreads();
+    for (unsigned k = 128; k > 0; k >>= 1) {
+        if (tid < k) sh[tid] = __dadd_rn(sh[tid], sh[tid + k]);
+        __syncthreads();
+    }
+    if (tid == 0) acc[0] = __dadd_rn(acc[0], sh[0]);
+}

@@ -1,0 +1,82 @@
+"""Host-side mirror of ``medpy.graphcut.generate.graph_from_voxels`` (reference:
+medpy/graphcut/generate.py:33-174).
+
+Same signature, same validation and the same order of operations -- regional term, boundary term, foreground
+markers, background markers (generate.py:159-172) -- but no edge list is built: the GCGraph handed to the
+term functions is a dense lattice in B200 HBM and each term is one CUDA kernel launch.
+"""
+import inspect
+import logging
+
+import numpy
+
+from .graph import GCGraph
+
+_logger = logging.getLogger("medpy_b200.graphcut")
+
+
+def voxel_edge_count(shape):
+    """Number of edges of the 2*ndim-connected lattice, size-1 axes dropped
+    (what the reference's ``__voxel_4conectedness`` computes, generate.py:363-383)."""
+    dims = [int(s) for s in shape if int(s) != 1]
+    total = 1
+    for s in dims:
+        total *= s
+    return sum((total // s) * (s - 1) for s in dims)
+
+
+def _noop_term(graph, term_args):
+    """Default for a missing term: same 2-parameter signature the reference's dummies have (generate.py:341-355)."""
+    return {}
+
+
+def _takes_two_parameters(fn):
+    return hasattr(fn, "__call__") and 2 == len(inspect.getfullargspec(fn)[0])
+
+
+def graph_from_voxels(fg_markers, bg_markers, regional_term=False, boundary_term=False,
+                      regional_term_args=False, boundary_term_args=False):
+    """Create a graph-cut ready graph from a voxel image.
+
+    Parameters and behaviour follow the reference (generate.py:33-110): ``fg_markers`` / ``bg_markers`` are
+    array-likes of one shape (converted to bool); ``regional_term`` / ``boundary_term`` are callables taking
+    exactly two positional parameters ``(graph, term_args)`` (``AttributeError`` otherwise); they receive a
+    ``GCGraph`` whose node ids are the C-order flat voxel indices.  Returns the solver-side graph object
+    (``graph.get_graph()``) offering ``maxflow()``, ``what_segment(i)`` and ``termtype``.
+
+    A voxel marked as both foreground and background receives both hard links, which cancel
+    (SURVEY.md App. A.5), exactly as in the reference.
+    """
+    fg_in = numpy.asarray(fg_markers)
+    _logger.debug("Assuming %d nodes and %d edges for image of shape %s", fg_in.size, voxel_edge_count(fg_in.shape), fg_in.shape)
+    graph = GCGraph(fg_in.size, voxel_edge_count(fg_in.shape), shape=fg_in.shape)
+
+    fg = numpy.asarray(fg_markers, dtype=numpy.bool_)
+    bg = numpy.asarray(bg_markers, dtype=numpy.bool_)
+
+    if not regional_term:
+        regional_term = _noop_term
+    if not boundary_term:
+        boundary_term = _noop_term
+
+    if not _takes_two_parameters(regional_term):
+        raise AttributeError("regional_term has to be a callable object which takes two parameter.")
+    if not _takes_two_parameters(boundary_term):
+        raise AttributeError("boundary_term has to be a callable object which takes two parameters.")
+
+    _logger.info("Computing and adding terminal edge weights...")
+    regional_term(graph, regional_term_args)
+
+    _logger.info("Computing and adding inter-node edge weights...")
+    boundary_term(graph, boundary_term_args)
+
+    _logger.info("Setting terminal weights for the markers...")
+    if bg.shape != fg.shape:
+        raise ValueError("fg_markers and bg_markers must have the same shape")
+    has_fg = bool(fg.any())
+    has_bg = bool(bg.any())
+    if has_fg or has_bg:
+        # set_source_nodes(fg ids) THEN set_sink_nodes(bg ids) (generate.py:169-172) as one fused device pass
+        graph._add_markers(fg if has_fg else None, bg if has_bg else None)
+
+    return graph.get_graph()

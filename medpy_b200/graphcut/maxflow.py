@@ -1,0 +1,265 @@
+"""``medpy_b200.graphcut.maxflow`` -- the object ``graph_from_voxels`` returns.
+
+Mirror of the reference's compiled module ``medpy.graphcut.maxflow`` (Boost.Python,
+lib/maxflow/src/wrapper.cpp:59-89): class ``GraphDouble`` with ``add_tweights / sum_edge / add_edge /
+maxflow / what_segment / get_edge / get_trcap / get_node_num / get_arc_num / reset`` and the nested enum
+``termtype`` (wrapper.cpp:85-88).  Storage is NOT the reference's node/arc lists: the graph is a dense
+2*ndim-connected lattice living in B200 HBM behind the C ABI (include/medpy_b200_graphcut.h); whole energy
+terms are handed to CUDA kernels, element-wise calls are staged in dense host arrays and uploaded in bulk.
+
+There is no CPU solver here: the first operation that needs the device creates the native graph and
+raises ``RuntimeError`` when no CUDA device / built extension is available.
+"""
+import enum
+
+import numpy
+
+__all__ = ["GraphDouble", "GraphFloat", "GraphInt"]
+
+
+class _termtype(enum.IntEnum):
+    """graph.h:57-61: terminals."""
+    SOURCE = 0
+    SINK = 1
+
+
+def _strides_of(shape):
+    st = []
+    acc = 1
+    for s in reversed(shape):
+        st.append(acc)
+        acc *= int(s)
+    return tuple(reversed(st))
+
+
+class GraphDouble:
+    """Lattice max-flow graph with the reference's ``GraphDouble`` method names.
+
+    ``GraphDouble(node_num_max, edge_num_max, shape=None)``: ``shape`` is the logical lattice shape (C-order
+    node ids, generate.py:170-172); without it the graph is a 1-D chain of ``node_num_max`` nodes.
+    """
+
+    termtype = _termtype
+
+    def __init__(self, node_num_max, edge_num_max=0, shape=None, device=-1):
+        if shape is None:
+            shape = (int(node_num_max),)
+        shape = tuple(int(s) for s in shape)
+        if len(shape) < 1 or len(shape) > 4:
+            raise ValueError("the lattice path supports 1 to 4 dimensions, got shape {}".format(shape))
+        n = 1
+        for s in shape:
+            n *= s
+        if n != int(node_num_max):
+            raise ValueError("shape {} does not hold {} nodes".format(shape, node_num_max))
+        self._shape = shape
+        self._n = n
+        self._strides = _strides_of(shape)
+        self._edges = int(edge_num_max)
+        self._device = device
+        self._native = None
+        # element-wise staging (dense host arrays, flushed in bulk)
+        self._st_src = None
+        self._st_snk = None
+        self._st_touched = None
+        self._st_nw = {}  # axis -> [fwd, bwd] dense arrays
+        self._mask = None
+        self._offlattice = None
+        self._pending = []
+
+    # ------------------------------------------------------------------ native handle
+    @property
+    def shape(self):
+        return self._shape
+
+    def _nat(self):
+        if self._native is None:
+            from .. import _lib  # raises ImportError loudly when the extension is not built
+            self._native = _lib.Graph(list(self._shape), self._device)
+        return self._native
+
+    def _dirty(self):
+        self._mask = None
+
+    # ------------------------------------------------------------------ staging of element-wise calls
+    # Element-wise calls (add_tweights / sum_edge, i.e. GCGraph.set_tweight / set_nweight / set_source_nodes)
+    # never touch the device: they fill dense host batches that are uploaded in call order by _flush().
+    def _close_tweight_batch(self):
+        if self._st_src is not None:
+            self._pending.append(("tw", self._st_src, self._st_snk))
+            self._st_src = self._st_snk = self._st_touched = None
+
+    def _open_tweight_batch(self):
+        if self._st_src is None:
+            self._st_src = numpy.zeros(self._n, dtype=numpy.float64)
+            self._st_snk = numpy.zeros(self._n, dtype=numpy.float64)
+            self._st_touched = numpy.zeros(self._n, dtype=numpy.bool_)
+
+    def stage_tweights_many(self, ids, cap_source, cap_sink):
+        """add_tweights(v, cap_source, cap_sink) for every v in ids, in order (ids already range-checked)."""
+        ids = numpy.asarray(ids, dtype=numpy.int64)
+        self._dirty()
+        self._open_tweight_batch()
+        if numpy.unique(ids).size == ids.size:
+            if self._st_touched[ids].any():
+                self._close_tweight_batch()
+                self._open_tweight_batch()
+            self._st_src[ids] = float(cap_source)
+            self._st_snk[ids] = float(cap_sink)
+            self._st_touched[ids] = True
+        else:
+            for v in ids:
+                self.add_tweights(int(v), cap_source, cap_sink)
+
+    def _flush(self):
+        self._close_tweight_batch()
+        if self._st_nw:
+            for axis in sorted(self._st_nw):
+                fwd, bwd = self._st_nw[axis]
+                self._pending.append(("nw", axis, fwd, bwd))
+            self._st_nw = {}
+        pending, self._pending = self._pending, []
+        for op in pending:
+            if op[0] == "tw":
+                self._nat().add_tweights_dense(op[1].reshape(self._shape), op[2].reshape(self._shape))
+            else:
+                # pairs never set stay 0, which sum_edge semantics allow (graph.h:456-463 asserts cap >= 0)
+                self._nat().add_nweights_dense(op[1], op[2].reshape(self._shape), op[3].reshape(self._shape))
+
+    # ------------------------------------------------------------------ bulk term entry points (used by energy_voxel)
+    def add_regional_probability(self, prob, alpha, compute_f32):
+        self._flush()
+        self._dirty()
+        self._nat().add_regional_probability(prob, float(alpha), bool(compute_f32))
+
+    def add_tweights_dense(self, src, snk):
+        self._flush()
+        self._dirty()
+        src = numpy.ascontiguousarray(src, dtype=numpy.float64).reshape(self._shape)
+        snk = numpy.ascontiguousarray(snk, dtype=numpy.float64).reshape(self._shape)
+        self._nat().add_tweights_dense(src, snk)
+
+    def add_markers(self, fg, bg):
+        self._flush()
+        self._dirty()
+        self._nat().add_markers(fg, bg)
+
+    def add_boundary(self, kind, image, sigma, spacing, norm):
+        self._flush()
+        self._dirty()
+        self._nat().add_boundary(int(kind), image, float(sigma), spacing, float(norm))
+
+    def add_nweights_dense(self, axis, fwd, bwd):
+        self._flush()
+        self._dirty()
+        self._nat().add_nweights_dense(int(axis), fwd, bwd)
+
+    # ------------------------------------------------------------------ reference GraphDouble API
+    def add_node(self, num=1):
+        """graph.h:388-413.  Nodes are implied by the lattice; returns the id the reference would."""
+        return 0
+
+    def add_tweights(self, i, cap_source, cap_sink):
+        """graph.h:415-425, staged: calls on distinct nodes are batched into one dense device pass."""
+        i = int(i)
+        if i < 0 or i >= self._n:
+            raise ValueError("Invalid node id of {}. Valid values are 0 to {}.".format(i, self._n - 1))
+        self._open_tweight_batch()
+        if self._st_touched[i]:
+            self._close_tweight_batch()  # add_tweights is order dependent per node: start a new batch
+            self._open_tweight_batch()
+        self._st_src[i] = float(cap_source)
+        self._st_snk[i] = float(cap_sink)
+        self._st_touched[i] = True
+        self._dirty()
+
+    def _axis_of(self, i, j):
+        d = j - i
+        for axis, st in enumerate(self._strides):
+            if abs(d) == st and self._shape[axis] > 1:
+                lo = min(i, j)
+                if (lo // st) % self._shape[axis] < self._shape[axis] - 1:
+                    return axis
+        return None
+
+    def sum_edge(self, i, j, cap, rev_cap):
+        """graph.h:456-480 for lattice neighbours (accumulating)."""
+        i, j = int(i), int(j)
+        if i < 0 or j < 0 or i >= self._n or j >= self._n or i == j:
+            raise ValueError("invalid node ids ({}, {})".format(i, j))
+        axis = self._axis_of(i, j)
+        if axis is None:
+            # accepted like the reference would, but it can never be solved here: general sparse graphs are
+            # outside the voxel path; maxflow() refuses.
+            self._offlattice = (i, j)
+            return
+        if axis not in self._st_nw:
+            self._st_nw[axis] = [numpy.zeros(self._n, dtype=numpy.float64), numpy.zeros(self._n, dtype=numpy.float64)]
+        fwd, bwd = self._st_nw[axis]
+        if i < j:
+            fwd[i] += float(cap)
+            bwd[i] += float(rev_cap)
+        else:
+            fwd[j] += float(rev_cap)
+            bwd[j] += float(cap)
+        self._dirty()
+
+    add_edge = sum_edge  # graph.h:427-454: parallel arcs act as summed capacities
+
+    def maxflow(self):
+        """Graph::maxflow (maxflow.cpp:471-604): min-cut energy including the add_tweights constants."""
+        if self._offlattice is not None:
+            raise NotImplementedError(
+                "edge {} does not join lattice neighbours of shape {}: general sparse graphs are outside the "
+                "voxel path (SURVEY.md §8 row f4)".format(self._offlattice, self._shape))
+        self._flush()
+        return self._nat().maxflow()
+
+    def get_mask(self):
+        """Bulk read-out: uint8 array of the lattice shape, 0 where what_segment == SINK else 1
+        (what bin/medpy_graphcut_voxel.py:177-181 builds voxel by voxel)."""
+        if self._mask is None:
+            self.maxflow()
+            self._mask = self._nat().get_mask()
+        return self._mask
+
+    def what_segment(self, i, default_segm=None):
+        """graph.h:560-571."""
+        m = self.get_mask()
+        i = int(i)
+        if i < 0 or i >= self._n:
+            raise ValueError("Invalid node id of {}. Valid values are 0 to {}.".format(i, self._n - 1))
+        return _termtype.SOURCE if m.flat[i] else _termtype.SINK
+
+    def reset(self):
+        self._st_src = self._st_snk = self._st_touched = None
+        self._st_nw = {}
+        self._mask = None
+        self._offlattice = None
+        self._pending = []
+        if self._native is not None:
+            self._native.reset()
+
+    def get_edge(self, i, j):
+        self._flush()
+        return self._nat().get_edge(int(i), int(j))
+
+    def get_trcap(self, i):
+        self._flush()
+        return self._nat().get_trcap(int(i))
+
+    def get_node_num(self):
+        return self._n
+
+    def get_arc_num(self):
+        self._flush()
+        return self._nat().get_arc_num()
+
+    def stats(self):
+        return self._nat().stats()
+
+
+# The reference module exports three instantiations (wrapper.cpp:8-10); only GraphDouble is used by the
+# Python layer (graph.py:26,305).  The other names resolve to the same lattice graph.
+GraphFloat = GraphDouble
+GraphInt = GraphDouble

@@ -60,7 +60,7 @@ def rms_neighbour_difference(image):
         step = max(1, (1 << 24) // max(1, int(numpy.prod(a.shape[1:]))))
         for i in range(0, a.shape[0], step):
             diff = a[i:i + step].astype(numpy.float64) - b[i:i + step].astype(numpy.float64)
-            acc += float(numpy.einsum("...,...->", diff, diff))
+            acc += float(numpy.dot(diff.ravel(), diff.ravel()))
             cnt += diff.size
     return float(numpy.sqrt(acc / max(cnt, 1)))
 
