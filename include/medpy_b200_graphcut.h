@@ -88,6 +88,9 @@ typedef struct mgc_stats {
     double flow_const;          /* sum of the add_tweights minima (graph.h:423)     */
     double energy;              /* value maxflow() returned                         */
     int64_t device_bytes;       /* device memory held by the handle                 */
+    double ms_push;             /* device ms inside push/relabel sweeps (CUDA events around each batch)  */
+    double ms_relabel;          /* device ms inside global-relabel kernels (init + relaxation sweeps)    */
+    double ms_boundary;         /* device ms of the last boundary (n-link) kernel alone                  */
 } mgc_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------- */

@@ -383,15 +383,18 @@ int relabel_relax(mgc_graph* g, int* any)
     *any = 0;
     for (;;) {
         CK(cudaMemsetAsync(g->d_flags + 1, 0, sizeof(int), g->stream));
+        cudaEventRecord(g->ev[2], g->stream);
         for (int i = 0; i < g->relax_batch; ++i) {
             if (g->nd == 3) k_relabel_relax<3><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S.rmask, g->S.height, g->d_flags + 1);
             else            k_relabel_relax<4><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S.rmask, g->S.height, g->d_flags + 1);
         }
         g->st.kernel_launches += g->relax_batch;
         g->st.relabel_sweeps += g->relax_batch;
+        cudaEventRecord(g->ev[3], g->stream);
         int changed = 0;
         CK(cudaMemcpyAsync(&changed, g->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
         CK(cudaStreamSynchronize(g->stream));
+        { float ms = 0; cudaEventElapsedTime(&ms, g->ev[2], g->ev[3]); g->st.ms_relabel += ms; }
         if (!changed) break;
         *any = 1;
     }
@@ -414,6 +417,7 @@ int count_active(mgc_graph* g, int64_t* out)
 // n push sweeps; *work_last = whether the last sweep still found an active voxel
 int push_sweeps(mgc_graph* g, int n, int* work_last)
 {
+    if (work_last) cudaEventRecord(g->ev[2], g->stream);
     for (int i = 0; i < n; ++i) {
         if (i == n - 1) CK(cudaMemsetAsync(g->d_flags + 2, 0, sizeof(int), g->stream));
         if (g->nd == 3) k_push<3, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, g->d_flags + 2);
@@ -423,8 +427,12 @@ int push_sweeps(mgc_graph* g, int n, int* work_last)
     g->st.push_sweeps += n;
     CK(cudaGetLastError());
     if (work_last) {
+        cudaEventRecord(g->ev[3], g->stream);
         CK(cudaMemcpyAsync(work_last, g->d_flags + 2, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
         CK(cudaStreamSynchronize(g->stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, g->ev[2], g->ev[3]);
+        g->st.ms_push += ms;
     }
     return MGC_OK;
 }
@@ -612,6 +620,7 @@ int mgc_add_boundary(mgc_graph* g, int32_t kind, const mgc_array* image, double 
         P.norm = (kind == MGC_BOUNDARY_MAXIMUM_LINEAR) ? mm[1] : mm[0];
     }
     CK(cudaMemsetAsync(g->d_flags, 0, sizeof(int), g->stream));
+    cudaEventRecord(g->ev[2], g->stream);
     switch (image->dtype) {
         case MGC_F32: boundary_launch<float>(g, (const float*)img, P); break;
         case MGC_F64: boundary_launch<double>(g, (const double*)img, P); break;
@@ -619,10 +628,12 @@ int mgc_add_boundary(mgc_graph* g, int32_t kind, const mgc_array* image, double 
         case MGC_I16: boundary_launch<int16_t>(g, (const int16_t*)img, P); break;
         case MGC_I32: boundary_launch<int32_t>(g, (const int32_t*)img, P); break;
     }
+    cudaEventRecord(g->ev[3], g->stream);
     CK(cudaGetLastError());
     int bad = 0;
     CK(cudaMemcpyAsync(&bad, g->d_flags, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
     t.stop_sync();
+    { float ms = 0; cudaEventElapsedTime(&ms, g->ev[2], g->ev[3]); g->st.ms_boundary = ms; }
     invalidate(g);
     g->has_nlinks = true;
     if (bad) FAIL(MGC_E_WEIGHT, "Negative or zero weights are not allowed.");
@@ -770,7 +781,10 @@ int mgc_get_trcap(mgc_graph* g, int64_t node, double* trcap)
     CK(cudaMemcpyAsync(&e, g->S.excess + node, sizeof(double), cudaMemcpyDeviceToHost, g->stream));
     CK(cudaMemcpyAsync(&s, g->S.sink + node, sizeof(double), cudaMemcpyDeviceToHost, g->stream));
     CK(cudaStreamSynchronize(g->stream));
-    *trcap = s > 0 ? -s : e;
+    double tr = 0;
+    CK(cudaMemcpyAsync(&tr, g->S.tr + node, sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    *trcap = (tr < 0 && -tr - s > 0) ? -(-tr - s) : e;
     return MGC_OK;
 }
 

@@ -20,19 +20,17 @@ __global__ void __launch_bounds__(256) k_init_state(Lattice L, State<T> S)
     unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= L.n) return;
     double tr = (double)S.tr[v];
-    double e = 0.0, s = 0.0;
+    double e = 0.0;
     if (tr > 0) {
         double out = 0.0;
 #pragma unroll
         for (int k = 0; k < 2 * ND; ++k) out = __dadd_ru(out, (double)S.cap[k][v]);
         e = tr < out ? tr : out;
         if (!(out == out)) e = tr;  // NaN capacities (zero-image linear terms): leave the link alone
-    } else if (tr < 0) {
-        s = -tr;
     }
     if (!owned(L, v)) e = 0.0;      // ghost planes of a z-slab start with an empty outbox
     S.excess[v] = (T)e;
-    S.sink[v] = (T)s;
+    S.sink[v] = (T)0;               // flow absorbed so far; the link's capacity is max(-tr, 0)
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -53,12 +51,17 @@ __global__ void __launch_bounds__(256) k_push(Lattice L, State<T> S, int* __rest
     if (!owned(L, v)) return;
     *work = 1;
     T pushed = 0;
-    T s = S.sink[v];
-    if (s > 0) {                      // the sink sits at height 0: always admissible
-        T d = e < s ? e : s;
-        S.sink[v] = s - d;
-        e -= d;
-        pushed += d;
+    T scap = -S.tr[v];                // capacity of the sink link (if any)
+    if (scap > 0) {                   // the sink sits at height 0: always admissible
+        T sf = S.sink[v];             // absorbed so far (kept as a sum of pushes: summing these gives the flow
+        T r = scap - sf;              //  without the 65535 - (65535 - tiny) cancellation a residual would have)
+        if (r > 0) {
+            T d;
+            if (e < r) { d = e; sf += d; } else { d = r; sf = scap; }   // saturation is exact
+            S.sink[v] = sf;
+            e -= d;
+            pushed += d;
+        }
     }
     if (e > 0) {
         T c[2 * ND];
@@ -108,7 +111,7 @@ __global__ void __launch_bounds__(256) k_relabel_init(Lattice L, State<T> S)
     S.rmask[v] = (uint8_t)m;
     // ghost planes restart at HINF: a from-scratch BFS must only ever see upper bounds, otherwise two slabs
     // can keep each other's stale finite labels alive (count-to-infinity) and the stop test never fires
-    S.height[v] = (owned(L, v) && S.sink[v] > 0) ? 1 : MGC_HINF;
+    S.height[v] = (owned(L, v) && (-S.tr[v]) - S.sink[v] > 0) ? 1 : MGC_HINF;
 }
 
 template <int ND>
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(256) k_mask(Lattice L, const int* __restrict__
     mask[v] = height[v] >= MGC_HINF ? 1 : 0;
 }
 
-// flow absorbed by the sink links of the owned voxels: sum(max(-tr,0) - sink_residual); deterministic
+// flow absorbed by the sink links of the owned voxels; deterministic
 template <typename T>
 __global__ void __launch_bounds__(256) k_absorbed(Lattice L, State<T> S, double* __restrict__ partials)
 {
@@ -166,8 +169,7 @@ __global__ void __launch_bounds__(256) k_absorbed(Lattice L, State<T> S, double*
     unsigned v = blockIdx.x * blockDim.x + tid;
     double a = 0.0;
     if (v < L.n && owned(L, v)) {
-        double tr = (double)S.tr[v];
-        if (tr < 0) a = __dsub_rn(-tr, (double)S.sink[v]);
+        a = (double)S.sink[v];
     }
     sh[tid] = a;
     __syncthreads();

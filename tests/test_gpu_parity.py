@@ -229,8 +229,9 @@ def test_element_wise_api_matches_bulk():
 
 
 def test_weights_not_positive_raise_value_error():
-    """fp32 image whose global min and max voxels are adjacent: 1 - x/M can go negative for the linear term ->
-    the reference raises ValueError from set_nweight; so do we."""
+    """GCGraph.set_nweight raises ValueError for weights <= 0 (graph.py:436-437).  The g-functions clamp
+    non-positive values to DBL_MIN, so the only way there is a non-positive spacing (energy_voxel.py:657-658);
+    an exact zero from the linear term becomes DBL_MIN and must NOT raise."""
     gc = _gc()
     img = numpy.zeros((4, 4), dtype=numpy.float64)
     img[0, 0] = 1.0
@@ -240,10 +241,10 @@ def test_weights_not_positive_raise_value_error():
     # x = 2, M = 2 -> weight exactly 0 -> DBL_MIN, fine
     g = gc.graph_from_voxels(fg, bg, boundary_term=gc.energy_voxel.boundary_difference_linear, boundary_term_args=(img, False))
     g.maxflow()
-    # division with negative sigma makes weights negative -> ValueError
+    assert g.get_edge(0, 1) == 2.2250738585072014e-308
     with pytest.raises(ValueError):
         gc.graph_from_voxels(fg, bg, boundary_term=gc.energy_voxel.boundary_difference_division,
-                             boundary_term_args=(img + 5, -0.5, False))
+                             boundary_term_args=(img, 0.5, (-1.0, 1.0)))
 
 
 def test_duality_certificate_256cubed():
