@@ -5,6 +5,7 @@
 #include "gc_common.cuh"
 #include "gc_terms.cuh"
 #include "gc_solver.cuh"
+#include "gc_tiles.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -108,6 +109,15 @@ struct mgc_graph {
     double energy = 0.0;
     std::vector<uint8_t> host_mask;
     bool host_mask_valid = false;
+
+    // tile solver (3-D lattices)
+    Tiles TL{};
+    bool use_tiles = false;
+    int* tflag = nullptr;              // push: tile may hold an active voxel
+    int* rflag[2] = {nullptr, nullptr};// relabel: tile must be (re)visited, double buffered
+    int* d_tcount = nullptr;           // [0],[1] relabel counters, [2] push still-active, [3] flag count
+    int tile_iters = 8;                // synchronous push/relabel rounds per tile visit
+    int passes0 = 1, passes_max = 8;   // two-colour passes per round: starts at passes0, doubles up to passes_max
 
     // tuning
     int sweeps_per_round = 32;
@@ -322,6 +332,20 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
     if (!rc) { rc = alloc_buf(g, 64, &p); g->d_scalars = (double*)p; }
     if (!rc) { rc = alloc_buf(g, 64, &p); g->d_flags = (int*)p; }
     if (!rc) { rc = alloc_buf(g, 64, &p); g->d_count = (unsigned long long*)p; }
+    if (!rc && g->nd == 3) {
+        for (int d = 0; d < 3; ++d) g->TL.nt[d] = (g->L.dim[d] + TILE - 1) / TILE;
+        g->TL.ntiles = g->TL.nt[0] * g->TL.nt[1] * g->TL.nt[2];
+        const size_t tb = (size_t)g->TL.ntiles * sizeof(int);
+        if (!rc) { rc = alloc_buf(g, tb, &p); g->tflag = (int*)p; }
+        if (!rc) { rc = alloc_buf(g, tb, &p); g->rflag[0] = (int*)p; }
+        if (!rc) { rc = alloc_buf(g, tb, &p); g->rflag[1] = (int*)p; }
+        if (!rc) { rc = alloc_buf(g, 64, &p); g->d_tcount = (int*)p; }
+        g->use_tiles = !slab;
+        if (const char* sv = getenv("MEDPY_GC_SOLVER")) if (!strcmp(sv, "v0")) g->use_tiles = false;
+        if (const char* e1 = getenv("MEDPY_GC_ITERS")) if (atoi(e1) > 0) g->tile_iters = atoi(e1);
+        if (const char* e2 = getenv("MEDPY_GC_PASSES0")) if (atoi(e2) > 0) g->passes0 = atoi(e2);
+        if (const char* e3 = getenv("MEDPY_GC_PASSES_MAX")) if (atoi(e3) > 0) g->passes_max = atoi(e3);
+    }
     if (rc) { g_create_error = g->err; mgc_destroy(g); return rc; }
     if (cudaStreamCreate(&g->stream) != cudaSuccess) { g_create_error = "cudaStreamCreate failed"; mgc_destroy(g); return MGC_E_CUDA; }
     g->own_stream = true;
@@ -433,6 +457,87 @@ int push_sweeps(mgc_graph* g, int n, int* work_last)
         float ms = 0;
         cudaEventElapsedTime(&ms, g->ev[2], g->ev[3]);
         g->st.ms_push += ms;
+    }
+    return MGC_OK;
+}
+
+// ---- tile solver driver --------------------------------------------------------------------------------
+int read_tcount(mgc_graph* g, int idx, int* out)
+{
+    CK(cudaMemcpyAsync(out, g->d_tcount + idx, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    return MGC_OK;
+}
+
+// exact global relabel by tile-wise relaxation; work is proportional to the tiles whose labels still move
+int relabel_tiles(mgc_graph* g)
+{
+    cudaEventRecord(g->ev[2], g->stream);
+    CK(cudaMemsetAsync(g->d_tcount, 0, 2 * sizeof(int), g->stream));
+    k_relabel_init_tile<double><<<g->TL.ntiles, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S, g->rflag[0], g->d_tcount);
+    g->st.kernel_launches++;
+    CK(cudaMemsetAsync(g->rflag[1], 0, (size_t)g->TL.ntiles * sizeof(int), g->stream));
+    int cur = 0;
+    for (;;) {
+        int pending = 0;
+        int rc = read_tcount(g, cur, &pending);
+        if (rc) return rc;
+        if (!pending) break;
+        for (int rep = 0; rep < 2; ++rep) {
+            CK(cudaMemsetAsync(g->d_tcount + (1 - cur), 0, sizeof(int), g->stream));
+            k_relabel_tile<<<g->TL.ntiles, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S.rmask, g->S.height, g->rflag[cur],
+                                                                    g->rflag[1 - cur], g->d_tcount + (1 - cur));
+            cur = 1 - cur;
+            g->st.kernel_launches++;
+            g->st.relabel_sweeps++;
+        }
+    }
+    CK(cudaGetLastError());
+    cudaEventRecord(g->ev[3], g->stream);
+    CK(cudaEventSynchronize(g->ev[3]));
+    { float ms = 0; cudaEventElapsedTime(&ms, g->ev[2], g->ev[3]); g->st.ms_relabel += ms; }
+    g->st.global_relabels++;
+    return MGC_OK;
+}
+
+// `passes` two-colour passes over the flagged tiles
+int push_tiles(mgc_graph* g, int passes)
+{
+    cudaEventRecord(g->ev[2], g->stream);
+    const int half = (g->TL.nt[2] + 1) / 2;
+    const int grid = g->TL.nt[0] * g->TL.nt[1] * half;
+    for (int p = 0; p < passes; ++p) {
+        k_push_tile<double><<<grid, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S, 0, g->tile_iters, g->tflag, nullptr);
+        k_push_tile<double><<<grid, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S, 1, g->tile_iters, g->tflag, nullptr);
+    }
+    g->st.kernel_launches += 2 * passes;
+    g->st.push_sweeps += passes;
+    CK(cudaGetLastError());
+    cudaEventRecord(g->ev[3], g->stream);
+    CK(cudaEventSynchronize(g->ev[3]));
+    { float ms = 0; cudaEventElapsedTime(&ms, g->ev[2], g->ev[3]); g->st.ms_push += ms; }
+    return MGC_OK;
+}
+
+int solve_tiles(mgc_graph* g)
+{
+    int rc = ensure_state(g);
+    if (rc) return rc;
+    k_fill_int<<<(g->TL.ntiles + 255) / 256, 256, 0, g->stream>>>(g->tflag, g->TL.ntiles, 1);
+    g->st.kernel_launches++;
+    int passes = g->passes0;
+    int64_t rounds = 0;
+    for (;;) {
+        rc = relabel_tiles(g);
+        if (rc) return rc;
+        int64_t active = 0;
+        rc = count_active(g, &active);
+        if (rc) return rc;
+        if (active == 0) break;
+        if (++rounds > g->max_rounds) FAIL(MGC_E_NOCONV, "push-relabel did not converge within the round cap");
+        rc = push_tiles(g, passes);
+        if (rc) return rc;
+        passes = passes * 2 > g->passes_max ? g->passes_max : passes * 2;
     }
     return MGC_OK;
 }
@@ -675,7 +780,12 @@ int mgc_maxflow(mgc_graph* g, double* energy)
     if (g->solved) { if (energy) *energy = g->energy; return MGC_OK; }
     {
         Timer t(g, &g->st.ms_solve);
-        int rc = ensure_state(g);
+        int rc = MGC_OK;
+        if (g->use_tiles) {
+            rc = solve_tiles(g);
+            if (rc) return rc;
+        } else {
+        rc = ensure_state(g);
         if (rc) return rc;
         int64_t rounds = 0;
         for (;;) {
@@ -701,6 +811,7 @@ int mgc_maxflow(mgc_graph* g, double* energy)
                 done += chunk;
                 if (!work) break;
             }
+        }
         }
         t.stop_sync();
     }

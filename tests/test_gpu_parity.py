@@ -240,8 +240,8 @@ def test_weights_not_positive_raise_value_error():
     bg = numpy.zeros((4, 4)); bg[0, 0] = 1
     # x = 2, M = 2 -> weight exactly 0 -> DBL_MIN, fine
     g = gc.graph_from_voxels(fg, bg, boundary_term=gc.energy_voxel.boundary_difference_linear, boundary_term_args=(img, False))
-    g.maxflow()
     assert g.get_edge(0, 1) == 2.2250738585072014e-308
+    g.maxflow()
     with pytest.raises(ValueError):
         gc.graph_from_voxels(fg, bg, boundary_term=gc.energy_voxel.boundary_difference_division,
                              boundary_term_args=(img, 0.5, (-1.0, 1.0)))
