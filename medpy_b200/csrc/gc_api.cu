@@ -103,6 +103,8 @@ struct mgc_graph {
     bool own_stream = false;
     cudaEvent_t ev[6] = {};
 
+    bool caps_fresh = true;            // capacity arrays not written yet since create/reset (hold garbage)
+    bool tr_fresh = true;              // same for tr[]
     bool state_init = false;
     bool solved = false;
     bool has_nlinks = false;
@@ -113,9 +115,13 @@ struct mgc_graph {
     // tile solver (3-D lattices)
     Tiles TL{};
     bool use_tiles = false;
-    int* tflag = nullptr;              // push: tile may hold an active voxel
-    int* rflag[2] = {nullptr, nullptr};// relabel: tile must be (re)visited, double buffered
-    int* d_tcount = nullptr;           // [0],[1] relabel counters, [2] push still-active, [3] flag count
+    int* pflag = nullptr;              // push: tile is already on the list its colour consumes next
+    int* rflag = nullptr;              // relabel: tile is already on the next relabel list
+    int* rl_items[2] = {nullptr, nullptr};     // relabel worklists (double buffered)
+    int* pl_items[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // push worklists [colour][buffer]
+    int* d_tcount = nullptr;           // [0..1] relabel counts, [2..5] push counts [colour*2+buffer], [8] cursor
+    int pl_sel[2] = {0, 0};            // buffer each colour consumes next
+    int n_ctas = 296;                  // persistent CTAs per tile-kernel launch
     int tile_iters = 8;                // synchronous push/relabel rounds per tile visit
     int passes0 = 1, passes_max = 8;   // two-colour passes per round: starts at passes0, doubles up to passes_max
 
@@ -336,10 +342,16 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
         for (int d = 0; d < 3; ++d) g->TL.nt[d] = (g->L.dim[d] + TILE - 1) / TILE;
         g->TL.ntiles = g->TL.nt[0] * g->TL.nt[1] * g->TL.nt[2];
         const size_t tb = (size_t)g->TL.ntiles * sizeof(int);
-        if (!rc) { rc = alloc_buf(g, tb, &p); g->tflag = (int*)p; }
-        if (!rc) { rc = alloc_buf(g, tb, &p); g->rflag[0] = (int*)p; }
-        if (!rc) { rc = alloc_buf(g, tb, &p); g->rflag[1] = (int*)p; }
+        if (!rc) { rc = alloc_buf(g, tb, &p); g->pflag = (int*)p; }
+        if (!rc) { rc = alloc_buf(g, tb, &p); g->rflag = (int*)p; }
+        for (int i = 0; i < 2 && !rc; ++i) { rc = alloc_buf(g, tb, &p); g->rl_items[i] = (int*)p; }
+        for (int i = 0; i < 4 && !rc; ++i) { rc = alloc_buf(g, tb, &p); g->pl_items[i >> 1][i & 1] = (int*)p; }
         if (!rc) { rc = alloc_buf(g, 64, &p); g->d_tcount = (int*)p; }
+        {
+            cudaDeviceProp prop{};
+            if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0)
+                g->n_ctas = 2 * prop.multiProcessorCount;   // k_push_tile is built for 2 CTAs per SM
+        }
         g->use_tiles = !slab;
         if (const char* sv = getenv("MEDPY_GC_SOLVER")) if (!strcmp(sv, "v0")) g->use_tiles = false;
         if (const char* e1 = getenv("MEDPY_GC_ITERS")) if (atoi(e1) > 0) g->tile_iters = atoi(e1);
@@ -362,8 +374,14 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
 template <typename E>
 int boundary_launch(mgc_graph* g, const E* img, const BoundaryParams& P)
 {
-    if (g->nd == 3) k_boundary<E, 3, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, img, P, g->d_flags);
-    else            k_boundary<E, 4, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, img, P, g->d_flags);
+    if (g->caps_fresh) {
+        if (g->nd == 3) k_boundary<E, 3, double, true><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, img, P, g->d_flags);
+        else            k_boundary<E, 4, double, true><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, img, P, g->d_flags);
+    } else {
+        if (g->nd == 3) k_boundary<E, 3, double, false><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, img, P, g->d_flags);
+        else            k_boundary<E, 4, double, false><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, img, P, g->d_flags);
+    }
+    g->caps_fresh = false;
     g->st.kernel_launches++;
     return MGC_OK;
 }
@@ -381,9 +399,25 @@ int minmax_launch(mgc_graph* g, const E* img)
     return MGC_OK;
 }
 
+// terms that were never given leave their arrays unwritten: zero them before anything reads them
+int materialise_zeros(mgc_graph* g)
+{
+    const size_t nb = (size_t)g->L.n;
+    if (g->caps_fresh) {
+        for (int k = 0; k < 2 * g->nd; ++k) CK(cudaMemsetAsync(g->S.cap[k], 0, nb * sizeof(double), g->stream));
+        g->caps_fresh = false;
+    }
+    if (g->tr_fresh) {
+        CK(cudaMemsetAsync(g->S.tr, 0, nb * sizeof(double), g->stream));
+        g->tr_fresh = false;
+    }
+    return MGC_OK;
+}
+
 int ensure_state(mgc_graph* g)
 {
     if (g->state_init) return MGC_OK;
+    { int rc0 = materialise_zeros(g); if (rc0) return rc0; }
     if (g->nd == 3) k_init_state<3, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S);
     else            k_init_state<4, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S);
     g->st.kernel_launches++;
@@ -462,6 +496,10 @@ int push_sweeps(mgc_graph* g, int n, int* work_last)
 }
 
 // ---- tile solver driver --------------------------------------------------------------------------------
+WorkList rl(mgc_graph* g, int i) { return WorkList{g->rl_items[i], g->d_tcount + i}; }
+WorkList pl(mgc_graph* g, int color, int buf) { return WorkList{g->pl_items[color][buf], g->d_tcount + 2 + color * 2 + buf}; }
+int* cursor(mgc_graph* g) { return g->d_tcount + 8; }
+
 int read_tcount(mgc_graph* g, int idx, int* out)
 {
     CK(cudaMemcpyAsync(out, g->d_tcount + idx, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
@@ -469,28 +507,43 @@ int read_tcount(mgc_graph* g, int idx, int* out)
     return MGC_OK;
 }
 
-// exact global relabel by tile-wise relaxation; work is proportional to the tiles whose labels still move
-int relabel_tiles(mgc_graph* g)
+// first call: solver state + first labels + first worklists in one pass (k_init_tile)
+int init_tiles(mgc_graph* g)
+{
+    CK(cudaMemsetAsync(g->d_tcount, 0, 64, g->stream));
+    g->pl_sel[0] = g->pl_sel[1] = 0;
+    k_init_tile<double><<<g->TL.ntiles, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S, g->rflag, rl(g, 0), g->pflag,
+                                                                  pl(g, 0, 0), pl(g, 1, 0));
+    g->st.kernel_launches++;
+    CK(cudaGetLastError());
+    g->state_init = true;
+    return MGC_OK;
+}
+
+// exact global relabel by tile-wise relaxation; work is proportional to the tiles whose labels still move.
+// `fresh` = the labels and list 0 were just produced by k_init_tile.
+int relabel_tiles(mgc_graph* g, bool fresh)
 {
     cudaEventRecord(g->ev[2], g->stream);
-    CK(cudaMemsetAsync(g->d_tcount, 0, 2 * sizeof(int), g->stream));
-    k_relabel_init_tile<double><<<g->TL.ntiles, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S, g->rflag[0], g->d_tcount);
-    g->st.kernel_launches++;
-    CK(cudaMemsetAsync(g->rflag[1], 0, (size_t)g->TL.ntiles * sizeof(int), g->stream));
+    if (!fresh) {
+        CK(cudaMemsetAsync(g->d_tcount, 0, 2 * sizeof(int), g->stream));
+        k_relabel_reset<<<g->TL.ntiles, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S.rmask, g->S.height, g->rflag, rl(g, 0));
+        g->st.kernel_launches++;
+    }
     int cur = 0;
     for (;;) {
         int pending = 0;
         int rc = read_tcount(g, cur, &pending);
         if (rc) return rc;
         if (!pending) break;
-        for (int rep = 0; rep < 2; ++rep) {
-            CK(cudaMemsetAsync(g->d_tcount + (1 - cur), 0, sizeof(int), g->stream));
-            k_relabel_tile<<<g->TL.ntiles, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S.rmask, g->S.height, g->rflag[cur],
-                                                                    g->rflag[1 - cur], g->d_tcount + (1 - cur));
-            cur = 1 - cur;
-            g->st.kernel_launches++;
-            g->st.relabel_sweeps++;
-        }
+        CK(cudaMemsetAsync(g->d_tcount + (1 - cur), 0, sizeof(int), g->stream));
+        CK(cudaMemsetAsync(cursor(g), 0, sizeof(int), g->stream));
+        const int grid = pending < g->n_ctas * 2 ? pending : g->n_ctas * 2;   // 4 KB smem: more CTAs per SM fit
+        k_relabel_tile<<<grid, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S.rmask, g->S.height, g->rflag, rl(g, cur),
+                                                         cursor(g), rl(g, 1 - cur));
+        cur = 1 - cur;
+        g->st.kernel_launches++;
+        g->st.relabel_sweeps++;
     }
     CK(cudaGetLastError());
     cudaEventRecord(g->ev[3], g->stream);
@@ -500,17 +553,29 @@ int relabel_tiles(mgc_graph* g)
     return MGC_OK;
 }
 
-// `passes` two-colour passes over the flagged tiles
+// one colour: consume its current list; still-active tiles go to its alternate list, receivers of cross-face flow
+// to the list the other colour consumes next
+int push_color(mgc_graph* g, int color)
+{
+    const int a = g->pl_sel[color], oa = g->pl_sel[1 - color];
+    CK(cudaMemsetAsync(cursor(g), 0, sizeof(int), g->stream));
+    k_push_tile<double><<<g->n_ctas, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S, g->tile_iters, g->pflag, pl(g, color, a),
+                                                               cursor(g), pl(g, color, 1 - a), pl(g, 1 - color, oa));
+    CK(cudaMemsetAsync(g->d_tcount + 2 + color * 2 + a, 0, sizeof(int), g->stream));   // consumed list is empty again
+    g->pl_sel[color] = 1 - a;
+    g->st.kernel_launches++;
+    return MGC_OK;
+}
+
 int push_tiles(mgc_graph* g, int passes)
 {
     cudaEventRecord(g->ev[2], g->stream);
-    const int half = (g->TL.nt[2] + 1) / 2;
-    const int grid = g->TL.nt[0] * g->TL.nt[1] * half;
     for (int p = 0; p < passes; ++p) {
-        k_push_tile<double><<<grid, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S, 0, g->tile_iters, g->tflag, nullptr);
-        k_push_tile<double><<<grid, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S, 1, g->tile_iters, g->tflag, nullptr);
+        int rc = push_color(g, 0);
+        if (rc) return rc;
+        rc = push_color(g, 1);
+        if (rc) return rc;
     }
-    g->st.kernel_launches += 2 * passes;
     g->st.push_sweeps += passes;
     CK(cudaGetLastError());
     cudaEventRecord(g->ev[3], g->stream);
@@ -519,19 +584,39 @@ int push_tiles(mgc_graph* g, int passes)
     return MGC_OK;
 }
 
+// active voxels, counted exactly over the two pending push lists (a superset of the tiles that can hold one)
+int count_active_tiles(mgc_graph* g, int64_t* out)
+{
+    CK(cudaMemsetAsync(g->d_count, 0, sizeof(unsigned long long), g->stream));
+    for (int color = 0; color < 2; ++color)
+        k_count_active_tiles<double><<<g->n_ctas * 2, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S, pl(g, color, g->pl_sel[color]), g->d_count);
+    g->st.kernel_launches += 2;
+    unsigned long long c = 0;
+    CK(cudaMemcpyAsync(&c, g->d_count, sizeof(c), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    *out = (int64_t)c;
+    g->st.active_last = (int64_t)c;
+    return MGC_OK;
+}
+
 int solve_tiles(mgc_graph* g)
 {
-    int rc = ensure_state(g);
+    int rc = materialise_zeros(g);
     if (rc) return rc;
-    k_fill_int<<<(g->TL.ntiles + 255) / 256, 256, 0, g->stream>>>(g->tflag, g->TL.ntiles, 1);
-    g->st.kernel_launches++;
+    bool fresh = false;
+    if (!g->state_init) {
+        rc = init_tiles(g);
+        if (rc) return rc;
+        fresh = true;
+    }
     int passes = g->passes0;
     int64_t rounds = 0;
     for (;;) {
-        rc = relabel_tiles(g);
+        rc = relabel_tiles(g, fresh);
         if (rc) return rc;
+        fresh = false;
         int64_t active = 0;
-        rc = count_active(g, &active);
+        rc = count_active_tiles(g, &active);
         if (rc) return rc;
         if (active == 0) break;
         if (++rounds > g->max_rounds) FAIL(MGC_E_NOCONV, "push-relabel did not converge within the round cap");
@@ -596,9 +681,9 @@ int mgc_reset(mgc_graph* g)
 {
     if (!g) return MGC_E_ARG;
     CK(cudaSetDevice(g->device));
-    const size_t nb = (size_t)g->L.n;
-    for (int k = 0; k < 2 * g->nd; ++k) CK(cudaMemsetAsync(g->S.cap[k], 0, nb * sizeof(double), g->stream));
-    CK(cudaMemsetAsync(g->S.tr, 0, nb * sizeof(double), g->stream));
+    // no memset of the big arrays: the first n-link / t-link term overwrites them (FRESH kernels)
+    g->caps_fresh = true;
+    g->tr_fresh = true;
     CK(cudaMemsetAsync(g->d_scalars, 0, 64, g->stream));
     CK(cudaMemsetAsync(g->d_flags, 0, 64, g->stream));
     invalidate(g);
@@ -637,9 +722,10 @@ int mgc_add_regional_probability(mgc_graph* g, const mgc_array* prob, double alp
     int rc = stage_input(g, prob, 0, &p);
     if (rc) return rc;
     if (prob->dtype == MGC_F32)
-        k_regional<float, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const float*)p, alpha, compute_dtype == MGC_F32, g->partials);
+        k_regional<float, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const float*)p, alpha, compute_dtype == MGC_F32, g->tr_fresh ? 1 : 0, g->partials);
     else
-        k_regional<double, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const double*)p, alpha, 0, g->partials);
+        k_regional<double, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const double*)p, alpha, 0, g->tr_fresh ? 1 : 0, g->partials);
+    g->tr_fresh = false;
     g->st.kernel_launches++;
     CK(cudaGetLastError());
     rc = finish_flow_const(g);
@@ -660,7 +746,8 @@ int mgc_add_tweights_dense(mgc_graph* g, const mgc_array* src, const mgc_array* 
     if (rc) return rc;
     rc = stage_input(g, snk, 1, &pk);
     if (rc) return rc;
-    k_tweights_dense<double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const double*)ps, (const double*)pk, g->partials);
+    k_tweights_dense<double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const double*)ps, (const double*)pk, g->tr_fresh ? 1 : 0, g->partials);
+    g->tr_fresh = false;
     g->st.kernel_launches++;
     CK(cudaGetLastError());
     rc = finish_flow_const(g);
@@ -681,7 +768,8 @@ int mgc_add_markers(mgc_graph* g, const mgc_array* fg, const mgc_array* bg)
     int rc = MGC_OK;
     if (fg) { rc = stage_input(g, fg, 0, &pf); if (rc) return rc; }
     if (bg) { rc = stage_input(g, bg, 1, &pb); if (rc) return rc; }
-    k_markers<double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const uint8_t*)pf, (const uint8_t*)pb, g->partials);
+    k_markers<double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const uint8_t*)pf, (const uint8_t*)pb, g->tr_fresh ? 1 : 0, g->partials);
+    g->tr_fresh = false;
     g->st.kernel_launches++;
     CK(cudaGetLastError());
     rc = finish_flow_const(g);
@@ -757,6 +845,11 @@ int mgc_add_nweights_dense(mgc_graph* g, int32_t axis, const mgc_array* fwd, con
     if (rc) return rc;
     rc = stage_input(g, bwd, 1, &pb);
     if (rc) return rc;
+    if (g->caps_fresh) {
+        const size_t nbz = (size_t)g->L.n;
+        for (int k = 0; k < 2 * g->nd; ++k) CK(cudaMemsetAsync(g->S.cap[k], 0, nbz * sizeof(double), g->stream));
+        g->caps_fresh = false;
+    }
     CK(cudaMemsetAsync(g->d_flags, 0, sizeof(int), g->stream));
     const int ca = axis + g->shift;
     if (g->nd == 3) k_nweights_dense<3, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, ca, (const double*)pf, (const double*)pb, g->d_flags);
@@ -862,6 +955,7 @@ int mgc_get_edge(mgc_graph* g, int64_t i, int64_t j, double* cap)
     const int64_t n = (int64_t)g->L.n;
     if (i < 0 || j < 0 || i >= n || j >= n || i == j) FAIL(MGC_E_ARG, "bad node ids");
     *cap = 0.0;
+    if (g->caps_fresh) return MGC_OK;
     int c[4] = {0, 0, 0, 0};
     unsigned r = (unsigned)i;
     for (int d = 0; d < g->nd; ++d) { c[d] = (int)(r / g->L.stride[d]); r %= g->L.stride[d]; }
@@ -883,6 +977,7 @@ int mgc_get_trcap(mgc_graph* g, int64_t node, double* trcap)
 {
     if (!g || !trcap) return MGC_E_ARG;
     if (node < 0 || node >= (int64_t)g->L.n) FAIL(MGC_E_ARG, "node id out of range");
+    if (g->tr_fresh) { *trcap = 0.0; return MGC_OK; }
     if (!g->state_init) {
         CK(cudaMemcpyAsync(trcap, g->S.tr + node, sizeof(double), cudaMemcpyDeviceToHost, g->stream));
         CK(cudaStreamSynchronize(g->stream));

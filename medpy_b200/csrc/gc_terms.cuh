@@ -142,7 +142,10 @@ __device__ __forceinline__ double g_weight(const BoundaryParams& P, double x)
 // and adds it to cap(p->q) [array 2d+1, index p] and cap(q->p) [array 2d, index q]; both stores are
 // coalesced because q = p + stride_d is contiguous in p.  `bad` is set if a weight <= 0 appears
 // (GCGraph.set_nweight raises ValueError there, graph.py:436-437; NaN passes, like the reference).
-template <typename E, int ND, typename T>
+// FRESH = the capacity arrays hold garbage (first n-link term after create/reset): every entry is then written
+// exactly once with plain stores -- arcs that would leave the lattice get 0 -- which saves the memset and the
+// read-modify-write (48 + 48 B/voxel in 3-D).
+template <typename E, int ND, typename T, bool FRESH>
 __global__ void __launch_bounds__(256)
 k_boundary(Lattice L, State<T> S, const E* __restrict__ img, BoundaryParams P, int* __restrict__ bad)
 {
@@ -163,9 +166,17 @@ k_boundary(Lattice L, State<T> S, const E* __restrict__ img, BoundaryParams P, i
             double w = g_weight(P, x);
             if (P.inv_spacing_on != 0.0) w = __ddiv_rn(w, P.spacing[d]);
             if (w <= 0.0) isbad = 1;
-            S.cap[2 * d + 1][p] += (T)w;
-            S.cap[2 * d][q] += (T)w;
+            if (FRESH) {
+                S.cap[2 * d + 1][p] = (T)w;
+                S.cap[2 * d][q] = (T)w;
+            } else {
+                S.cap[2 * d + 1][p] += (T)w;
+                S.cap[2 * d][q] += (T)w;
+            }
+        } else if (FRESH) {
+            S.cap[2 * d + 1][p] = (T)0;      // no neighbour in +d
         }
+        if (FRESH && c[d] == 0) S.cap[2 * d][p] = (T)0;   // no neighbour in -d
     }
     if (isbad) *bad = 1;
 }
@@ -216,7 +227,7 @@ __device__ __forceinline__ void block_sum_store(double x, double* __restrict__ p
 // regional_probability_map (energy_voxel.py:62-65): products formed in the map's dtype when F32 != 0
 template <typename E, typename T>
 __global__ void __launch_bounds__(256)
-k_regional(Lattice L, State<T> S, const E* __restrict__ prob, double alpha, int compute_f32, double* __restrict__ partials)
+k_regional(Lattice L, State<T> S, const E* __restrict__ prob, double alpha, int compute_f32, int fresh, double* __restrict__ partials)
 {
     unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
     double m = 0.0;
@@ -232,7 +243,7 @@ k_regional(Lattice L, State<T> S, const E* __restrict__ prob, double alpha, int 
             s = __dmul_rn(p, alpha);
             t = __dmul_rn(__dsub_rn(1.0, p), alpha);
         }
-        T tr = S.tr[v];
+        T tr = fresh ? (T)0 : S.tr[v];      // fresh: tr[] holds garbage (first t-link term after create/reset)
         double mm = add_tweights_dev(tr, s, t);
         S.tr[v] = tr;
         if (owned(L, v)) m = mm;
@@ -243,12 +254,12 @@ k_regional(Lattice L, State<T> S, const E* __restrict__ prob, double alpha, int 
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_tweights_dense(Lattice L, State<T> S, const double* __restrict__ src, const double* __restrict__ snk,
-                 double* __restrict__ partials)
+                 int fresh, double* __restrict__ partials)
 {
     unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
     double m = 0.0;
     if (v < L.n) {
-        T tr = S.tr[v];
+        T tr = fresh ? (T)0 : S.tr[v];
         double mm = add_tweights_dev(tr, src[v], snk[v]);
         S.tr[v] = tr;
         if (owned(L, v)) m = mm;
@@ -260,14 +271,14 @@ k_tweights_dense(Lattice L, State<T> S, const double* __restrict__ src, const do
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_markers(Lattice L, State<T> S, const uint8_t* __restrict__ fg, const uint8_t* __restrict__ bg,
-          double* __restrict__ partials)
+          int fresh, double* __restrict__ partials)
 {
     unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
     double m = 0.0;
     if (v < L.n) {
         bool f = fg && fg[v], b = bg && bg[v];
-        if (f || b) {
-            T tr = S.tr[v];
+        if (f || b || fresh) {
+            T tr = fresh ? (T)0 : S.tr[v];
             double mm = 0.0;
             if (f) mm = add_tweights_dev(tr, 65535.0, 0.0);
             if (b) mm = __dadd_rn(mm, add_tweights_dev(tr, 0.0, 65535.0));

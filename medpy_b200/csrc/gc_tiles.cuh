@@ -1,19 +1,27 @@
 // gc_tiles.cuh -- tile-resident solver kernels for the 3-D lattice (the production path; gc_solver.cuh keeps
-// the per-voxel kernels used for 4-D lattices and as an A/B reference).
+// the per-voxel kernels used for 4-D lattices, z-slabs and as an A/B reference).
 //
-// The lattice is cut into 8x8x8 tiles; one 512-thread CTA owns one tile for the duration of a visit, keeps
-// the tile's state in shared memory (heights with a 1-voxel halo; for the push kernel also the six residual
-// capacity planes and the excess) and iterates there, so a visit costs one read and one write of the tile in
-// HBM however many push/relabel or relaxation rounds it takes.  Work is driven by per-tile flags: a tile is
-// visited only if it may hold work (an active voxel / a label that may still drop).
+// The lattice is cut into 8x8x8 tiles.  A 512-thread CTA owns one tile for the duration of a visit, keeps the
+// tile's state on chip (heights with a 1-voxel halo in shared memory; in the push kernel the six residual
+// capacities, excess and sink-link state of each voxel in its thread's registers) and iterates there, so a
+// visit costs one read and one write of the tile in HBM however many push/relabel or relaxation rounds it
+// takes.  Work is driven by per-tile WORKLISTS: persistent CTAs (a small multiple of the SM count) pull tile
+// ids from a device-side list with an atomic cursor; a tile is listed only if it may hold work (an active
+// voxel / a label that may still drop), and kernels append to the list of the next pass themselves.
 //
-//  * k_relabel_init_tile / k_relabel_tile : exact backward BFS from the sink (global relabel).  Heights only
-//    decrease during it, so tiles can run concurrently with benign races on the halo; a tile whose border
-//    labels dropped flags its face neighbours for the next pass.
-//  * k_push_tile : push/relabel discharge of one tile, several synchronous rounds in shared memory.  Tiles are
-//    processed in two colours (3-D checkerboard): tiles of one colour are never face-adjacent, so a running tile
-//    is the only writer of its own voxels and of its neighbours' border state, except that corner/edge
-//    voxels of an idle tile can receive from up to three running tiles at once -> neighbour excess uses atomics.
+//  * k_init_tile          : solver state from the terms (source-excess clamp, residual mask, first labels) and
+//                           the first worklists, fused in one pass over the lattice.
+//  * k_relabel_reset      : start of a later global relabel: labels from the residual mask, new worklist.
+//  * k_relabel_tile       : exact backward BFS from the sink (global relabel).  Labels only decrease during it,
+//                           so tiles run concurrently with benign races on the halo; a tile whose border labels
+//                           dropped lists its face neighbours for the next pass.
+//  * k_push_tile          : push/relabel discharge of one tile: synchronous rounds, "push then pull" through a
+//                           shared-memory outflow buffer, so every state update is made by the voxel's own
+//                           thread -- no shared-memory atomics, deterministic inside the tile.  Tiles are
+//                           processed in two colours (3-D checkerboard): tiles of one colour are never
+//                           face-adjacent, so a running tile is the only writer of its own voxels; flow
+//                           crossing a face lands in the idle neighbour's arrays with global atomics (a corner
+//                           voxel can receive from up to three running tiles).
 #pragma once
 #include "gc_common.cuh"
 
@@ -21,25 +29,32 @@
 #define TILE_VOX 512
 #define HALO_DIM 10
 #define HALO_VOX 1000
+#define RM_SINK 0x40u   // bit 6 of rmask: residual capacity towards the sink
 
 struct Tiles {
     int nt[3];      // tiles along z, y, x
     int ntiles;
 };
 
+// worklists: items[] + count; kernels consume `cur` through an atomic cursor and append to `next`
+struct WorkList {
+    int* items;
+    int* count;
+};
+
 __device__ __forceinline__ int hidx(int z, int y, int x) { return (z * HALO_DIM + y) * HALO_DIM + x; }
 
-// offsets in the halo cube for direction k (axis 0 = z slowest)
-__device__ __forceinline__ int hoff(int k)
+template <int K>
+__device__ __forceinline__ int hoff()
 {
-    const int s = (k >> 1) == 0 ? HALO_DIM * HALO_DIM : ((k >> 1) == 1 ? HALO_DIM : 1);
-    return (k & 1) ? s : -s;
+    constexpr int s = (K >> 1) == 0 ? HALO_DIM * HALO_DIM : ((K >> 1) == 1 ? HALO_DIM : 1);
+    return (K & 1) ? s : -s;
 }
 
 struct TileCtx {
+    int t;                 // tile id
     int tz, ty, tx;        // tile coordinates
     int lz, ly, lx;        // local coordinates of this thread's voxel
-    int gz, gy, gx;        // global coordinates
     bool inb;              // voxel inside the lattice
     bool own;              // ... and owned (not a ghost plane of a z-slab)
     unsigned v;            // flat index (valid when inb)
@@ -48,17 +63,27 @@ struct TileCtx {
 __device__ __forceinline__ TileCtx tile_ctx(const Lattice& L, const Tiles& TL, int t)
 {
     TileCtx c;
+    c.t = t;
     c.tx = t % TL.nt[2];
     int r = t / TL.nt[2];
     c.ty = r % TL.nt[1];
     c.tz = r / TL.nt[1];
     const int tid = threadIdx.x;
     c.lx = tid & 7; c.ly = (tid >> 3) & 7; c.lz = tid >> 6;
-    c.gz = c.tz * TILE + c.lz; c.gy = c.ty * TILE + c.ly; c.gx = c.tx * TILE + c.lx;
-    c.inb = c.gz < L.dim[0] && c.gy < L.dim[1] && c.gx < L.dim[2];
-    c.v = c.inb ? (unsigned)c.gz * L.stride[0] + (unsigned)c.gy * L.stride[1] + (unsigned)c.gx : 0u;
-    c.own = c.inb && c.gz >= L.own0 && c.gz < L.own1;
+    const int gz = c.tz * TILE + c.lz, gy = c.ty * TILE + c.ly, gx = c.tx * TILE + c.lx;
+    c.inb = gz < L.dim[0] && gy < L.dim[1] && gx < L.dim[2];
+    c.v = c.inb ? (unsigned)gz * L.stride[0] + (unsigned)gy * L.stride[1] + (unsigned)gx : 0u;
+    c.own = c.inb && gz >= L.own0 && gz < L.own1;
     return c;
+}
+
+__device__ __forceinline__ int tile_color(const TileCtx& c) { return (c.tz + c.ty + c.tx) & 1; }
+
+// neighbour tile id across face k (only valid if it exists)
+__device__ __forceinline__ int tile_nbr(const Tiles& TL, int t, int k)
+{
+    const int s = (k >> 1) == 0 ? TL.nt[1] * TL.nt[2] : ((k >> 1) == 1 ? TL.nt[2] : 1);
+    return (k & 1) ? t + s : t - s;
 }
 
 // cooperative load of heights (own voxel + the six halo faces) into the 10^3 cube; out-of-lattice -> HINF
@@ -87,197 +112,281 @@ __device__ __forceinline__ int load_heights(const Lattice& L, const TileCtx& c, 
     return h0;
 }
 
-__device__ __forceinline__ void flag_tile(int* __restrict__ flags, int* __restrict__ counter, int t)
+// append tile t to a worklist unless it is already flagged
+__device__ __forceinline__ void list_push(int* __restrict__ flags, const WorkList& wl, int t)
 {
-    if (atomicExch(&flags[t], 1) == 0 && counter) atomicAdd(counter, 1);
+    if (atomicExch(&flags[t], 1) == 0) wl.items[atomicAdd(wl.count, 1)] = t;
 }
 
-// ---------------------------------------------------------------------------------------------------
-// global relabel, tile form
-// ---------------------------------------------------------------------------------------------------
-// init: residual bit mask, label 1 for voxels with a residual sink link else HINF; flag tiles that hold a voxel
-// which still has to find its distance (unlabelled but with residual out-arcs).
-template <typename T>
-__global__ void __launch_bounds__(TILE_VOX) k_relabel_init_tile(Lattice L, Tiles TL, State<T> S, int* __restrict__ flags,
-                                                                int* __restrict__ counter)
+// persistent-CTA work fetch: returns the next tile id of `cur`, or -1 when the list is exhausted
+__device__ __forceinline__ int fetch_tile(const WorkList& cur, int* __restrict__ cursor, int* s_slot)
 {
-    const int t = blockIdx.x;
-    const TileCtx c = tile_ctx(L, TL, t);
-    int needs = 0;
-    if (c.inb) {
-        unsigned m = 0;
-#pragma unroll
-        for (int k = 0; k < 6; ++k)
-            if (S.cap[k][c.v] > 0) m |= 1u << k;
-        S.rmask[c.v] = (uint8_t)m;
-        // ghost planes restart at HINF as well (see k_relabel_init)
-        const int h = (c.own && (-S.tr[c.v]) - S.sink[c.v] > 0) ? 1 : MGC_HINF;
-        S.height[c.v] = h;
-        needs = (c.own && m != 0 && h == MGC_HINF) ? 1 : 0;
-    }
-    const int any = __syncthreads_or(needs);
+    __syncthreads();                       // previous tile fully done (also protects s_slot reuse)
     if (threadIdx.x == 0) {
-        flags[t] = any;
-        if (any) atomicAdd(counter, 1);
+        const int i = atomicAdd(cursor, 1);
+        *s_slot = (i < *cur.count) ? cur.items[i] : -1;
     }
-}
-
-// one visit: relax inside the tile until nothing changes, write back, wake the face neighbours whose halo changed
-__global__ void __launch_bounds__(TILE_VOX) k_relabel_tile(Lattice L, Tiles TL, const uint8_t* __restrict__ rmask,
-                                                           int* __restrict__ height, int* __restrict__ flag_cur,
-                                                           int* __restrict__ flag_next, int* __restrict__ counter_next)
-{
-    __shared__ int sh[HALO_VOX];
-    const int t = blockIdx.x;
-    if (flag_cur[t] == 0) return;
-    const TileCtx c = tile_ctx(L, TL, t);
-    const int h0 = load_heights(L, c, height, sh);
-    const unsigned m = c.own ? rmask[c.v] : 0u;
     __syncthreads();
-    if (threadIdx.x == 0) flag_cur[t] = 0;
-    const int me = hidx(c.lz + 1, c.ly + 1, c.lx + 1);
-    int h = h0;
-    for (;;) {
-        int changed = 0;
-        if (m && h > 1) {
-            int best = h;
-#pragma unroll
-            for (int k = 0; k < 6; ++k)
-                if (m & (1u << k)) { const int hw = sh[me + hoff(k)] + 1; best = hw < best ? hw : best; }
-            if (best < h) { h = best; sh[me] = h; changed = 1; }
-        }
-        if (!__syncthreads_or(changed)) break;
-    }
-    if (h != h0) {
-        height[c.v] = h;
-        if (c.lz == 0 && c.tz > 0) flag_tile(flag_next, counter_next, t - TL.nt[1] * TL.nt[2]);
-        if (c.lz == TILE - 1 && c.tz + 1 < TL.nt[0]) flag_tile(flag_next, counter_next, t + TL.nt[1] * TL.nt[2]);
-        if (c.ly == 0 && c.ty > 0) flag_tile(flag_next, counter_next, t - TL.nt[2]);
-        if (c.ly == TILE - 1 && c.ty + 1 < TL.nt[1]) flag_tile(flag_next, counter_next, t + TL.nt[2]);
-        if (c.lx == 0 && c.tx > 0) flag_tile(flag_next, counter_next, t - 1);
-        if (c.lx == TILE - 1 && c.tx + 1 < TL.nt[2]) flag_tile(flag_next, counter_next, t + 1);
-    }
+    return *s_slot;
 }
 
 // ---------------------------------------------------------------------------------------------------
-// push / relabel, tile form (one colour of the 3-D checkerboard per launch)
+// init: one pass over every tile after the terms are in
+//   excess = min(max(tr,0), roundup(sum of out-capacities))   (source-link clamp)
+//   sink[] = 0 (flow absorbed so far), rmask, first labels (1 where a sink link exists, else HINF)
+//   relabel worklist <- tiles holding an unlabelled voxel with residual out-arcs
+//   push worklists   <- tiles holding a voxel with excess
 // ---------------------------------------------------------------------------------------------------
-// grid: nt[0] * nt[1] * ceil(nt[2] / 2) blocks; block b of colour `color` maps to the tile whose x index has the
-// parity that makes (tz + ty + tx) & 1 == color.
 template <typename T>
-__global__ void __launch_bounds__(TILE_VOX) k_push_tile(Lattice L, Tiles TL, State<T> S, int color, int iters,
-                                                        int* __restrict__ tflag, int* __restrict__ n_still_active)
+__global__ void __launch_bounds__(TILE_VOX) k_init_tile(Lattice L, Tiles TL, State<T> S, int* __restrict__ rflag, WorkList rl,
+                                                        int* __restrict__ pflag, WorkList pl0, WorkList pl1)
 {
-    __shared__ T s_cap[6 * TILE_VOX];
-    __shared__ T s_exc[TILE_VOX];
-    __shared__ int s_h[HALO_VOX];
-
-    const int half = (TL.nt[2] + 1) >> 1;
-    const int bx = blockIdx.x % half;
-    const int r = blockIdx.x / half;
-    const int tyy = r % TL.nt[1], tzz = r / TL.nt[1];
-    const int txx = 2 * bx + ((tzz + tyy + color) & 1);
-    if (txx >= TL.nt[2]) return;
-    const int t = (tzz * TL.nt[1] + tyy) * TL.nt[2] + txx;
-    if (tflag[t] == 0) return;
-
-    const TileCtx c = tile_ctx(L, TL, t);
-    const int tid = threadIdx.x;
-    const int me = hidx(c.lz + 1, c.ly + 1, c.lx + 1);
-    const int h0 = load_heights(L, c, S.height, s_h);
-    T e0 = 0, c0[6], scap = 0, sf0 = 0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) { c0[k] = c.inb ? S.cap[k][c.v] : (T)0; s_cap[k * TILE_VOX + tid] = c0[k]; }
+    const TileCtx c = tile_ctx(L, TL, blockIdx.x);
+    int needs = 0, hasexc = 0;
     if (c.inb) {
-        e0 = S.excess[c.v];
-        const T tr = S.tr[c.v];
-        if (tr < 0) { scap = -tr; sf0 = S.sink[c.v]; }
-    }
-    s_exc[tid] = e0;
-    T sf = sf0;
-    int h = h0;
-    __syncthreads();
-    if (tid == 0) tflag[t] = 0;
-
-    // neighbour bookkeeping: local index inside the tile or, for a halo voxel, its global index and tile
-    for (int it = 0; it < iters; ++it) {
-        const T e_in = s_exc[tid];
-        int act = (c.own && e_in > 0 && h < MGC_HINF) ? 1 : 0;
-        if (act) {
-            T e = e_in, pushed = 0;
-            if (scap > 0) {
-                const T rr = scap - sf;
-                if (rr > 0) {
-                    T d;
-                    if (e < rr) { d = e; sf += d; } else { d = rr; sf = scap; }
-                    e -= d; pushed += d;
-                }
-            }
-            int newh = h;
-            if (e > 0) {
-                T cc[6];
-                int hn[6];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    cc[k] = s_cap[k * TILE_VOX + tid];
-                    hn[k] = cc[k] > 0 ? s_h[me + hoff(k)] : MGC_HINF;
-                }
-#pragma unroll 1
-                for (int rep = 0; rep < 6; ++rep) {
-                    int kb = -1, hb = MGC_HINF;
-#pragma unroll
-                    for (int k = 0; k < 6; ++k)
-                        if (cc[k] > 0 && hn[k] < hb) { hb = hn[k]; kb = k; }
-                    if (kb < 0) { newh = MGC_HINF; break; }
-                    if (hb >= h) { newh = hb + 1; break; }
-                    const T d = e < cc[kb] ? e : cc[kb];
-                    // where does the arc lead?
-                    const int ax = kb >> 1, sgn = (kb & 1) ? 1 : -1;
-                    const int lc = (ax == 0 ? c.lz : (ax == 1 ? c.ly : c.lx)) + sgn;
-                    atomicAdd(&s_cap[kb * TILE_VOX + tid], -d);
-                    if (lc >= 0 && lc < TILE) {
-                        const int wt = tid + sgn * (ax == 0 ? 64 : (ax == 1 ? 8 : 1));
-                        atomicAdd(&s_cap[(kb ^ 1) * TILE_VOX + wt], d);
-                        atomicAdd(&s_exc[wt], d);
-                    } else {
-                        const unsigned w = (unsigned)((int)c.v + dir_offset(L, kb));
-                        atomicAdd(&S.cap[kb ^ 1][w], d);
-                        atomicAdd(&S.excess[w], d);
-                        const int nt_ = t + sgn * (ax == 0 ? TL.nt[1] * TL.nt[2] : (ax == 1 ? TL.nt[2] : 1));
-                        tflag[nt_] = 1;
-                    }
-                    e -= d; pushed += d;
-                    cc[kb] = 0;
-                    if (!(e > 0)) break;
-                }
-            }
-            if (newh != h) { h = newh; s_h[me] = h; }
-            if (pushed > 0) atomicAdd(&s_exc[tid], -pushed);
-        }
-        if (!__syncthreads_or(act)) break;
-    }
-
-    // write back what changed (this CTA is the only writer of its own voxels during this launch)
-    const T e1 = s_exc[tid];
-    if (c.inb) {
-        if (e1 != e0) S.excess[c.v] = e1;
+        const double tr = (double)S.tr[c.v];
+        unsigned m = 0;
+        double out = 0.0;
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-            const T ck = s_cap[k * TILE_VOX + tid];
-            if (ck != c0[k]) S.cap[k][c.v] = ck;
+            const double ck = (double)S.cap[k][c.v];
+            if (ck > 0) m |= 1u << k;
+            out = __dadd_ru(out, ck);
         }
-        if (h != h0) S.height[c.v] = h;
-        if (sf != sf0) S.sink[c.v] = sf;
+        double e = 0.0;
+        if (tr > 0) { e = tr < out ? tr : out; if (!(out == out)) e = tr; }
+        if (tr < 0) m |= RM_SINK;
+        if (!c.own) e = 0.0;
+        S.excess[c.v] = (T)e;
+        S.sink[c.v] = (T)0;
+        S.rmask[c.v] = (uint8_t)m;
+        const int h = (c.own && tr < 0) ? 1 : MGC_HINF;
+        S.height[c.v] = h;
+        needs = (c.own && (m & 0x3fu) != 0 && h == MGC_HINF) ? 1 : 0;
+        hasexc = e > 0 ? 1 : 0;
     }
-    const int still = (c.own && e1 > 0 && h < MGC_HINF) ? 1 : 0;
-    if (__syncthreads_or(still) && tid == 0) {
-        tflag[t] = 1;
-        if (n_still_active) atomicAdd(n_still_active, 1);
+    const int any_needs = __syncthreads_or(needs);
+    const int any_exc = __syncthreads_or(hasexc);
+    if (threadIdx.x == 0) {
+        rflag[c.t] = any_needs;
+        if (any_needs) rl.items[atomicAdd(rl.count, 1)] = c.t;
+        pflag[c.t] = any_exc;
+        if (any_exc) {
+            const WorkList& pl = tile_color(c) ? pl1 : pl0;
+            pl.items[atomicAdd(pl.count, 1)] = c.t;
+        }
     }
 }
 
-__global__ void k_fill_int(int* __restrict__ p, int n, int val)
+// later global relabels: labels from the (incrementally maintained) residual mask; 5 B/voxel
+__global__ void __launch_bounds__(TILE_VOX) k_relabel_reset(Lattice L, Tiles TL, const uint8_t* __restrict__ rmask,
+                                                            int* __restrict__ height, int* __restrict__ rflag, WorkList rl)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = val;
+    const TileCtx c = tile_ctx(L, TL, blockIdx.x);
+    int needs = 0;
+    if (c.inb) {
+        const unsigned m = rmask[c.v];
+        const int h = (c.own && (m & RM_SINK)) ? 1 : MGC_HINF;
+        height[c.v] = h;
+        needs = (c.own && (m & 0x3fu) != 0 && h == MGC_HINF) ? 1 : 0;
+    }
+    const int any_needs = __syncthreads_or(needs);
+    if (threadIdx.x == 0) {
+        rflag[c.t] = any_needs;
+        if (any_needs) rl.items[atomicAdd(rl.count, 1)] = c.t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// global relabel pass: persistent CTAs over the current worklist
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE_VOX) k_relabel_tile(Lattice L, Tiles TL, const uint8_t* __restrict__ rmask,
+                                                           int* __restrict__ height, int* __restrict__ rflag,
+                                                           WorkList cur, int* __restrict__ cursor, WorkList next)
+{
+    __shared__ int sh[HALO_VOX];
+    __shared__ int s_slot;
+    for (;;) {
+        const int t = fetch_tile(cur, cursor, &s_slot);
+        if (t < 0) break;
+        const TileCtx c = tile_ctx(L, TL, t);
+        if (threadIdx.x == 0) rflag[t] = 0;        // may be listed again by a neighbour from now on
+        const int h0 = load_heights(L, c, height, sh);
+        const unsigned m = c.own ? (rmask[c.v] & 0x3fu) : 0u;
+        __syncthreads();
+        const int me = hidx(c.lz + 1, c.ly + 1, c.lx + 1);
+        int h = h0;
+        for (;;) {
+            int changed = 0;
+            if (m && h > 1) {
+                int best = h;
+                if (m & 1u)  { const int hw = sh[me + hoff<0>()] + 1; best = hw < best ? hw : best; }
+                if (m & 2u)  { const int hw = sh[me + hoff<1>()] + 1; best = hw < best ? hw : best; }
+                if (m & 4u)  { const int hw = sh[me + hoff<2>()] + 1; best = hw < best ? hw : best; }
+                if (m & 8u)  { const int hw = sh[me + hoff<3>()] + 1; best = hw < best ? hw : best; }
+                if (m & 16u) { const int hw = sh[me + hoff<4>()] + 1; best = hw < best ? hw : best; }
+                if (m & 32u) { const int hw = sh[me + hoff<5>()] + 1; best = hw < best ? hw : best; }
+                if (best < h) { h = best; sh[me] = h; changed = 1; }
+            }
+            if (!__syncthreads_or(changed)) break;
+        }
+        if (h != h0) {
+            height[c.v] = h;
+            if (c.lz == 0 && c.tz > 0) list_push(rflag, next, tile_nbr(TL, t, 0));
+            if (c.lz == TILE - 1 && c.tz + 1 < TL.nt[0]) list_push(rflag, next, tile_nbr(TL, t, 1));
+            if (c.ly == 0 && c.ty > 0) list_push(rflag, next, tile_nbr(TL, t, 2));
+            if (c.ly == TILE - 1 && c.ty + 1 < TL.nt[1]) list_push(rflag, next, tile_nbr(TL, t, 3));
+            if (c.lx == 0 && c.tx > 0) list_push(rflag, next, tile_nbr(TL, t, 4));
+            if (c.lx == TILE - 1 && c.tx + 1 < TL.nt[2]) list_push(rflag, next, tile_nbr(TL, t, 5));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// push / relabel discharge of the tiles of one colour (persistent CTAs over that colour's worklist)
+// ---------------------------------------------------------------------------------------------------
+// One direction of the push phase.  K is a compile-time direction so everything stays in registers.
+template <int K, typename T>
+__device__ __forceinline__ void push_dir(const Lattice& L, const Tiles& TL, const State<T>& S, const TileCtx& c,
+                                         const int* s_h, T* s_out, int me, int h, T& e, T& ck, int& minh,
+                                         int* __restrict__ pflag, const WorkList& other_next, unsigned& nbr_listed,
+                                         unsigned& dirty)
+{
+    T d = 0;
+    if (ck > 0) {
+        const int hw = s_h[me + hoff<K>()];
+        if (hw < h && e > 0) {
+            d = e < ck ? e : ck;
+            ck -= d;
+            e -= d;
+            dirty |= (1u << K) | 64u;
+        }
+        if (ck > 0) minh = hw < minh ? hw : minh;
+    }
+    constexpr int AX = K >> 1;
+    const int lc = (AX == 0 ? c.lz : (AX == 1 ? c.ly : c.lx)) + ((K & 1) ? 1 : -1);
+    const bool inside = lc >= 0 && lc < TILE;
+    if (inside) {
+        s_out[K * TILE_VOX + threadIdx.x] = d;         // pulled by the neighbour's own thread
+    } else if (d > 0) {
+        // the neighbour tile has the other colour and is idle: update its voxel in HBM
+        const unsigned w = (unsigned)((int)c.v + dir_offset(L, K));
+        atomicAdd(&S.cap[K ^ 1][w], d);
+        atomicAdd(&S.excess[w], d);
+        // its residual mask gains the reverse arc (byte-wise OR through the containing 32-bit word)
+        atomicOr(reinterpret_cast<unsigned*>(S.rmask) + (w >> 2), (1u << (K ^ 1)) << (8u * (w & 3u)));
+        if (!(nbr_listed & (1u << K))) { nbr_listed |= 1u << K; list_push(pflag, other_next, tile_nbr(TL, c.t, K)); }
+    }
+}
+
+template <int K, typename T>
+__device__ __forceinline__ void pull_dir(const TileCtx& c, const T* s_out, T& e, T& ck, unsigned& dirty)
+{
+    constexpr int AX = K >> 1;
+    constexpr int SG = (K & 1) ? 1 : -1;
+    const int lc = (AX == 0 ? c.lz : (AX == 1 ? c.ly : c.lx)) + SG;
+    if (lc >= 0 && lc < TILE) {
+        constexpr int ST = AX == 0 ? 64 : (AX == 1 ? 8 : 1);
+        // what my neighbour in direction K pushed towards me travelled along ITS direction K^1
+        const T d = s_out[(K ^ 1) * TILE_VOX + (int)threadIdx.x + SG * ST];
+        if (d > 0) {
+            e += d;
+            ck += d;   // my arc towards that neighbour is the reverse arc: it gains residual capacity
+            dirty |= (1u << K) | 64u;
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TILE_VOX, 2) k_push_tile(Lattice L, Tiles TL, State<T> S, int iters,
+                                                           int* __restrict__ pflag, WorkList cur, int* __restrict__ cursor,
+                                                           WorkList self_next, WorkList other_next)
+{
+    __shared__ T s_out[6 * TILE_VOX];
+    __shared__ int s_h[HALO_VOX];
+    __shared__ int s_slot;
+    for (;;) {
+        const int t = fetch_tile(cur, cursor, &s_slot);
+        if (t < 0) break;
+        const TileCtx c = tile_ctx(L, TL, t);
+        const int tid = threadIdx.x;
+        const int me = hidx(c.lz + 1, c.ly + 1, c.lx + 1);
+        if (tid == 0) pflag[t] = 0;
+        const int h0 = load_heights(L, c, S.height, s_h);
+        T e = 0, scap = 0, sf = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
+        if (c.inb) {
+            e = S.excess[c.v];
+            c0 = S.cap[0][c.v]; c1 = S.cap[1][c.v]; c2 = S.cap[2][c.v];
+            c3 = S.cap[3][c.v]; c4 = S.cap[4][c.v]; c5 = S.cap[5][c.v];
+            const T tr = S.tr[c.v];
+            if (tr < 0) { scap = -tr; sf = S.sink[c.v]; }
+        }
+        int h = h0;
+        unsigned nbr_listed = 0, dirty = 0;     // dirty: bit k = cap k changed, 64 = excess, 128 = sink flow
+        __syncthreads();
+
+        for (int it = 0; it < iters; ++it) {
+            // ---- push phase: decisions from the label snapshot, own registers updated, outflow published ----
+            const int act = (c.own && e > 0 && h < MGC_HINF) ? 1 : 0;
+            int newh = h;
+            if (act) {
+                if (scap > 0) {                      // the sink sits at height 0: always admissible
+                    const T rr = scap - sf;
+                    if (rr > 0) {
+                        if (e < rr) { sf += e; e = 0; } else { e -= rr; sf = scap; }   // saturation is exact
+                        dirty |= 64u | 128u;
+                    }
+                }
+                int minh = MGC_HINF;
+                push_dir<0>(L, TL, S, c, s_h, s_out, me, h, e, c0, minh, pflag, other_next, nbr_listed, dirty);
+                push_dir<1>(L, TL, S, c, s_h, s_out, me, h, e, c1, minh, pflag, other_next, nbr_listed, dirty);
+                push_dir<2>(L, TL, S, c, s_h, s_out, me, h, e, c2, minh, pflag, other_next, nbr_listed, dirty);
+                push_dir<3>(L, TL, S, c, s_h, s_out, me, h, e, c3, minh, pflag, other_next, nbr_listed, dirty);
+                push_dir<4>(L, TL, S, c, s_h, s_out, me, h, e, c4, minh, pflag, other_next, nbr_listed, dirty);
+                push_dir<5>(L, TL, S, c, s_h, s_out, me, h, e, c5, minh, pflag, other_next, nbr_listed, dirty);
+                // excess left => no admissible arc left => relabel above the lowest residual neighbour
+                if (e > 0) newh = (minh >= MGC_HINF) ? MGC_HINF : minh + 1;
+            } else {
+                s_out[0 * TILE_VOX + tid] = 0; s_out[1 * TILE_VOX + tid] = 0; s_out[2 * TILE_VOX + tid] = 0;
+                s_out[3 * TILE_VOX + tid] = 0; s_out[4 * TILE_VOX + tid] = 0; s_out[5 * TILE_VOX + tid] = 0;
+            }
+            if (!__syncthreads_or(act)) break;       // nothing moved in this tile: done
+            // ---- pull phase: every voxel collects what its in-tile neighbours sent; labels are published ----
+            pull_dir<0>(c, s_out, e, c0, dirty); pull_dir<1>(c, s_out, e, c1, dirty); pull_dir<2>(c, s_out, e, c2, dirty);
+            pull_dir<3>(c, s_out, e, c3, dirty); pull_dir<4>(c, s_out, e, c4, dirty); pull_dir<5>(c, s_out, e, c5, dirty);
+            if (newh != h) { h = newh; s_h[me] = h; }
+            __syncthreads();
+        }
+
+        // ---- write back what changed (this CTA is the only writer of its own voxels during this launch) ----
+        if (c.inb && (dirty || h != h0)) {
+            if (dirty & 64u) S.excess[c.v] = e;
+            if (dirty & 1u) S.cap[0][c.v] = c0;
+            if (dirty & 2u) S.cap[1][c.v] = c1;
+            if (dirty & 4u) S.cap[2][c.v] = c2;
+            if (dirty & 8u) S.cap[3][c.v] = c3;
+            if (dirty & 16u) S.cap[4][c.v] = c4;
+            if (dirty & 32u) S.cap[5][c.v] = c5;
+            if (h != h0) S.height[c.v] = h;
+            if (dirty & 128u) S.sink[c.v] = sf;
+            unsigned m = (c0 > 0 ? 1u : 0u) | (c1 > 0 ? 2u : 0u) | (c2 > 0 ? 4u : 0u) | (c3 > 0 ? 8u : 0u) |
+                         (c4 > 0 ? 16u : 0u) | (c5 > 0 ? 32u : 0u) | ((scap - sf > 0) ? RM_SINK : 0u);
+            S.rmask[c.v] = (uint8_t)m;
+        }
+        const int still = (c.own && e > 0 && h < MGC_HINF) ? 1 : 0;
+        if (__syncthreads_or(still) && tid == 0) list_push(pflag, self_next, t);
+    }
+}
+
+// exact count of active voxels, scanning only the tiles of a worklist (a superset of the tiles that can hold one)
+template <typename T>
+__global__ void __launch_bounds__(TILE_VOX) k_count_active_tiles(Lattice L, Tiles TL, State<T> S, WorkList wl,
+                                                                 unsigned long long* __restrict__ count)
+{
+    for (int i = blockIdx.x; i < *wl.count; i += gridDim.x) {
+        const TileCtx c = tile_ctx(L, TL, wl.items[i]);
+        const bool act = c.own && (S.excess[c.v] > 0) && (S.height[c.v] < MGC_HINF);
+        const unsigned b = __ballot_sync(0xffffffffu, act);
+        if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, (unsigned long long)__popc(b));
+    }
 }
