@@ -168,18 +168,20 @@ int mgc_get_stats(const mgc_graph* g, mgc_stats* out);
 int mgc_slab_plane_elems(const mgc_graph* g, int64_t* n);
 /* Initialise the solver state (source-excess clamp, sink capacities) once all terms are in. */
 int mgc_slab_begin(mgc_graph* g);
-/* `n` local push/relabel sweeps. */
+/* `n` local push/relabel passes (tile solver: two-colour passes; per-voxel solver: sweeps). */
 int mgc_slab_push(mgc_graph* g, int32_t n);
 /* Pack the messages for the lower / upper neighbour into device buffers of plane_elems elements each:
  * heights (int32) of my border plane and the flow (double) pushed across the border since the last pack.
  * Pass NULL for a side without neighbour. */
 int mgc_slab_pack(mgc_graph* g, int32_t* h_lo, double* f_lo, int32_t* h_hi, double* f_hi);
 /* Apply the neighbours' messages: ghost-plane heights, and received flow added to excess and to the reverse
- * residual of my border plane. */
-int mgc_slab_unpack(mgc_graph* g, const int32_t* h_lo, const double* f_lo, const int32_t* h_hi, const double* f_hi);
+ * residual of my border plane.  *ghost_changed_out = 1 if any ghost label differs from before. */
+int mgc_slab_unpack(mgc_graph* g, const int32_t* h_lo, const double* f_lo, const int32_t* h_hi, const double* f_hi,
+                    int32_t* ghost_changed_out);
 /* Global relabel, distributed: (re)start a backward BFS from the sink ... */
 int mgc_slab_relabel_begin(mgc_graph* g);
-/* ... relax locally until nothing changes; *changed_out = 1 if any height changed in this call. */
+/* ... relax locally until nothing changes (given the current ghost labels); *changed_out = 1 if any label
+ * changed in this call. */
 int mgc_slab_relabel_relax(mgc_graph* g, int32_t* changed_out);
 /* Voxels with excess > 0 and a finite label (owned planes only). */
 int mgc_slab_count_active(mgc_graph* g, int64_t* active_out);

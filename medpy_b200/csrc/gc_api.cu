@@ -121,6 +121,8 @@ struct mgc_graph {
     int* pl_items[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // push worklists [colour][buffer]
     int* d_tcount = nullptr;           // [0..1] relabel counts, [2..5] push counts [colour*2+buffer], [8] cursor
     int pl_sel[2] = {0, 0};            // buffer each colour consumes next
+    int rl_cur = 0;                    // relabel list consumed next
+    bool labels_fresh = false;         // labels + relabel list 0 come straight from k_init_tile
     int n_ctas = 296;                  // persistent CTAs per tile-kernel launch
     int tile_iters = 8;                // synchronous push/relabel rounds per tile visit
     int passes0 = 1, passes_max = 8;   // two-colour passes per round: starts at passes0, doubles up to passes_max
@@ -352,7 +354,7 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
             if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0)
                 g->n_ctas = 2 * prop.multiProcessorCount;   // k_push_tile is built for 2 CTAs per SM
         }
-        g->use_tiles = !slab;
+        g->use_tiles = true;
         if (const char* sv = getenv("MEDPY_GC_SOLVER")) if (!strcmp(sv, "v0")) g->use_tiles = false;
         if (const char* e1 = getenv("MEDPY_GC_ITERS")) if (atoi(e1) > 0) g->tile_iters = atoi(e1);
         if (const char* e2 = getenv("MEDPY_GC_PASSES0")) if (atoi(e2) > 0) g->passes0 = atoi(e2);
@@ -517,35 +519,56 @@ int init_tiles(mgc_graph* g)
     g->st.kernel_launches++;
     CK(cudaGetLastError());
     g->state_init = true;
+    g->labels_fresh = true;
+    g->rl_cur = 0;
     return MGC_OK;
 }
 
 // exact global relabel by tile-wise relaxation; work is proportional to the tiles whose labels still move.
-// `fresh` = the labels and list 0 were just produced by k_init_tile.
-int relabel_tiles(mgc_graph* g, bool fresh)
+// begin: labels from the residual mask + a fresh worklist (skipped when k_init_tile just produced both)
+int relabel_tiles_begin(mgc_graph* g)
 {
-    cudaEventRecord(g->ev[2], g->stream);
-    if (!fresh) {
-        CK(cudaMemsetAsync(g->d_tcount, 0, 2 * sizeof(int), g->stream));
-        k_relabel_reset<<<g->TL.ntiles, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S.rmask, g->S.height, g->rflag, rl(g, 0));
-        g->st.kernel_launches++;
-    }
-    int cur = 0;
+    if (g->labels_fresh) { g->labels_fresh = false; g->rl_cur = 0; return MGC_OK; }
+    CK(cudaMemsetAsync(g->d_tcount, 0, 2 * sizeof(int), g->stream));
+    k_relabel_reset<<<g->TL.ntiles, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S.rmask, g->S.height, g->rflag, rl(g, 0));
+    g->st.kernel_launches++;
+    g->rl_cur = 0;
+    CK(cudaGetLastError());
+    return MGC_OK;
+}
+
+// run passes until the current worklist is empty; *any = 1 if any tile was visited
+int relabel_tiles_run(mgc_graph* g, int* any)
+{
+    *any = 0;
     for (;;) {
+        const int cur = g->rl_cur;
         int pending = 0;
         int rc = read_tcount(g, cur, &pending);
         if (rc) return rc;
         if (!pending) break;
+        *any = 1;
         CK(cudaMemsetAsync(g->d_tcount + (1 - cur), 0, sizeof(int), g->stream));
         CK(cudaMemsetAsync(cursor(g), 0, sizeof(int), g->stream));
         const int grid = pending < g->n_ctas * 2 ? pending : g->n_ctas * 2;   // 4 KB smem: more CTAs per SM fit
         k_relabel_tile<<<grid, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S.rmask, g->S.height, g->rflag, rl(g, cur),
                                                          cursor(g), rl(g, 1 - cur));
-        cur = 1 - cur;
+        g->rl_cur = 1 - cur;
         g->st.kernel_launches++;
         g->st.relabel_sweeps++;
     }
     CK(cudaGetLastError());
+    return MGC_OK;
+}
+
+int relabel_tiles(mgc_graph* g)
+{
+    cudaEventRecord(g->ev[2], g->stream);
+    int rc = relabel_tiles_begin(g);
+    if (rc) return rc;
+    int any = 0;
+    rc = relabel_tiles_run(g, &any);
+    if (rc) return rc;
     cudaEventRecord(g->ev[3], g->stream);
     CK(cudaEventSynchronize(g->ev[3]));
     { float ms = 0; cudaEventElapsedTime(&ms, g->ev[2], g->ev[3]); g->st.ms_relabel += ms; }
@@ -603,18 +626,15 @@ int solve_tiles(mgc_graph* g)
 {
     int rc = materialise_zeros(g);
     if (rc) return rc;
-    bool fresh = false;
     if (!g->state_init) {
         rc = init_tiles(g);
         if (rc) return rc;
-        fresh = true;
     }
     int passes = g->passes0;
     int64_t rounds = 0;
     for (;;) {
-        rc = relabel_tiles(g, fresh);
+        rc = relabel_tiles(g);
         if (rc) return rc;
-        fresh = false;
         int64_t active = 0;
         rc = count_active_tiles(g, &active);
         if (rc) return rc;
@@ -1033,6 +1053,11 @@ int mgc_slab_begin(mgc_graph* g)
 {
     if (!g) return MGC_E_ARG;
     CK(cudaSetDevice(g->device));
+    if (g->use_tiles) {
+        int rc = materialise_zeros(g);
+        if (rc) return rc;
+        return g->state_init ? MGC_OK : init_tiles(g);
+    }
     return ensure_state(g);
 }
 
@@ -1041,6 +1066,7 @@ int mgc_slab_push(mgc_graph* g, int32_t n)
     if (!g || n < 0) return MGC_E_ARG;
     if (!g->state_init) FAIL(MGC_E_STATE, "call mgc_slab_begin first");
     CK(cudaSetDevice(g->device));
+    if (g->use_tiles) return push_tiles(g, n);
     return push_sweeps(g, n, nullptr);
 }
 
@@ -1064,24 +1090,39 @@ int mgc_slab_pack(mgc_graph* g, int32_t* h_lo, double* f_lo, int32_t* h_hi, doub
     return MGC_OK;
 }
 
-int mgc_slab_unpack(mgc_graph* g, const int32_t* h_lo, const double* f_lo, const int32_t* h_hi, const double* f_hi)
+int mgc_slab_unpack(mgc_graph* g, const int32_t* h_lo, const double* f_lo, const int32_t* h_hi, const double* f_hi,
+                    int32_t* ghost_changed_out)
 {
     if (!g) return MGC_E_ARG;
     CK(cudaSetDevice(g->device));
     const unsigned P = g->L.plane;
     const unsigned nb = (P + 255u) / 256u;
-    if (g->ghost_lo && h_lo && f_lo) {
-        const size_t border = (size_t)g->L.own0 * P, ghost = border - P;
-        // my arc border -> lower ghost is direction 0 (axis 0, -1)
-        k_slab_unpack<double><<<nb, 256, 0, g->stream>>>(P, g->S.height + ghost, g->S.excess + border, g->S.cap[0] + border, h_lo, f_lo, g->d_flags + 1);
-        g->st.kernel_launches++;
-    }
-    if (g->ghost_hi && h_hi && f_hi) {
-        const size_t border = (size_t)(g->L.own1 - 1) * P, ghost = border + P;
-        k_slab_unpack<double><<<nb, 256, 0, g->stream>>>(P, g->S.height + ghost, g->S.excess + border, g->S.cap[1] + border, h_hi, f_hi, g->d_flags + 1);
+    CK(cudaMemsetAsync(g->d_flags + 1, 0, sizeof(int), g->stream));
+    for (int side = 0; side < 2; ++side) {
+        const bool have = side == 0 ? (g->ghost_lo && h_lo && f_lo) : (g->ghost_hi && h_hi && f_hi);
+        if (!have) continue;
+        const int zb = side == 0 ? g->L.own0 : g->L.own1 - 1;
+        const int zg = side == 0 ? zb - 1 : zb + 1;
+        const int k = side == 0 ? 0 : 1;     // my arc border -> ghost: axis 0, -1 (lo) or +1 (hi)
+        const int32_t* hin = side == 0 ? h_lo : h_hi;
+        const double* fin = side == 0 ? f_lo : f_hi;
+        if (g->use_tiles) {
+            k_slab_unpack_tiles<double><<<nb, 256, 0, g->stream>>>(g->L, g->TL, g->S, zg, zb, k, hin, fin, g->rflag, rl(g, g->rl_cur),
+                                                                  g->pflag, pl(g, 0, g->pl_sel[0]), pl(g, 1, g->pl_sel[1]), g->d_flags + 1);
+        } else {
+            const size_t border = (size_t)zb * P, ghost = (size_t)zg * P;
+            k_slab_unpack<double><<<nb, 256, 0, g->stream>>>(P, g->S.height + ghost, g->S.excess + border, g->S.cap[k] + border,
+                                                            hin, fin, g->d_flags + 1);
+        }
         g->st.kernel_launches++;
     }
     CK(cudaGetLastError());
+    if (ghost_changed_out) {
+        int ch = 0;
+        CK(cudaMemcpyAsync(&ch, g->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+        CK(cudaStreamSynchronize(g->stream));
+        *ghost_changed_out = ch;
+    }
     return MGC_OK;
 }
 
@@ -1091,6 +1132,7 @@ int mgc_slab_relabel_begin(mgc_graph* g)
     if (!g->state_init) FAIL(MGC_E_STATE, "call mgc_slab_begin first");
     CK(cudaSetDevice(g->device));
     g->st.global_relabels++;
+    if (g->use_tiles) return relabel_tiles_begin(g);
     return relabel_init(g);
 }
 
@@ -1098,14 +1140,10 @@ int mgc_slab_relabel_relax(mgc_graph* g, int32_t* changed_out)
 {
     if (!g || !changed_out) return MGC_E_ARG;
     CK(cudaSetDevice(g->device));
-    // a ghost height changed by the preceding unpack counts as a change
-    int pre = 0;
-    CK(cudaMemcpyAsync(&pre, g->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
-    CK(cudaStreamSynchronize(g->stream));
     int any = 0;
-    int rc = relabel_relax(g, &any);
+    int rc = g->use_tiles ? relabel_tiles_run(g, &any) : relabel_relax(g, &any);
     if (rc) return rc;
-    *changed_out = (any || pre) ? 1 : 0;
+    *changed_out = any ? 1 : 0;
     return MGC_OK;
 }
 
@@ -1113,7 +1151,7 @@ int mgc_slab_count_active(mgc_graph* g, int64_t* active_out)
 {
     if (!g || !active_out) return MGC_E_ARG;
     CK(cudaSetDevice(g->device));
-    return count_active(g, active_out);
+    return g->use_tiles ? count_active_tiles(g, active_out) : count_active(g, active_out);
 }
 
 int mgc_slab_finish(mgc_graph* g, double* energy_part)

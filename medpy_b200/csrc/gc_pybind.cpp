@@ -210,11 +210,13 @@ public:
         { py::gil_scoped_release rel; rc = mgc_slab_pack(g_, (int32_t*)hlo, (double*)flo, (int32_t*)hhi, (double*)fhi); }
         check(rc, g_);
     }
-    void slab_unpack(uintptr_t hlo, uintptr_t flo, uintptr_t hhi, uintptr_t fhi)
+    int slab_unpack(uintptr_t hlo, uintptr_t flo, uintptr_t hhi, uintptr_t fhi)
     {
         int rc;
-        { py::gil_scoped_release rel; rc = mgc_slab_unpack(g_, (const int32_t*)hlo, (const double*)flo, (const int32_t*)hhi, (const double*)fhi); }
+        int32_t changed = 0;
+        { py::gil_scoped_release rel; rc = mgc_slab_unpack(g_, (const int32_t*)hlo, (const double*)flo, (const int32_t*)hhi, (const double*)fhi, &changed); }
         check(rc, g_);
+        return changed;
     }
     void slab_relabel_begin() { int rc; { py::gil_scoped_release rel; rc = mgc_slab_relabel_begin(g_); } check(rc, g_); }
     int slab_relabel_relax() { int32_t c = 0; int rc; { py::gil_scoped_release rel; rc = mgc_slab_relabel_relax(g_, &c); } check(rc, g_); return c; }

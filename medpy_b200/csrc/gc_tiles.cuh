@@ -390,3 +390,37 @@ __global__ void __launch_bounds__(TILE_VOX) k_count_active_tiles(Lattice L, Tile
         if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, (unsigned long long)__popc(b));
     }
 }
+
+// ---------------------------------------------------------------------------------------------------
+// z-slab border messages, tile-aware: besides applying the neighbour's message (see k_slab_unpack) the
+// receiving tiles are put on the worklists -- the relabel list when a ghost label changed, the push list of
+// the tile's colour when flow arrived -- and the border voxel's residual mask gains the arc towards the ghost.
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_slab_unpack_tiles(Lattice L, Tiles TL, State<T> S, int z_ghost, int z_border, int k_border_to_ghost,
+                                    const int* __restrict__ h_in, const double* __restrict__ f_in,
+                                    int* __restrict__ rflag, WorkList rl, int* __restrict__ pflag, WorkList pl0, WorkList pl1,
+                                    int* __restrict__ changed)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.plane) return;
+    const int y = (int)(i / L.stride[1]), x = (int)(i % L.stride[1]);
+    const unsigned vg = (unsigned)z_ghost * L.plane + i, vb = (unsigned)z_border * L.plane + i;
+    const int tg = ((z_ghost / TILE) * TL.nt[1] + y / TILE) * TL.nt[2] + x / TILE;
+    const int tb = ((z_border / TILE) * TL.nt[1] + y / TILE) * TL.nt[2] + x / TILE;
+    const int hn = h_in[i];
+    if (S.height[vg] != hn) {
+        S.height[vg] = hn;
+        *changed = 1;
+        list_push(rflag, rl, tb);
+        if (tg != tb) list_push(rflag, rl, tg);
+    }
+    const double f = f_in[i];
+    if (f > 0) {
+        S.excess[vb] += (T)f;
+        S.cap[k_border_to_ghost][vb] += (T)f;
+        S.rmask[vb] |= (uint8_t)(1u << k_border_to_ghost);
+        const int color = ((z_border / TILE) + y / TILE + x / TILE) & 1;
+        list_push(pflag, color ? pl1 : pl0, tb);
+    }
+}

@@ -1,0 +1,321 @@
+"""z-slab multi-GPU graph cut: one process per GPU, ``torch.distributed`` (NCCL over NVLink) for the plumbing.
+
+The global lattice is split into contiguous slabs along axis 0; rank r owns planes ``[z0, z1)`` and keeps one
+ghost plane per interior side.  Arcs crossing a slab border belong to their tail voxel; a push across the
+border parks the flow in the ghost plane (the rank's outbox) and the neighbour receives, per exchange, the
+border plane's labels (int32) and the parked flow (float64) -- one message per direction -- and adds the flow
+to the excess of its border voxel and to the residual of the reverse arc.  Labels used across a
+border are one exchange stale, which keeps every push feasible but not the labelling valid; correctness rests
+on the stop test only: after an EXACT distributed global relabel (local BFS to a fixed point <-> border label
+exchange, repeated until no ghost label changes anywhere), no voxel with excess has a finite label.
+
+The stepping primitives are the ``mgc_slab_*`` entry points of the C ABI; this module only sequences them and
+moves the border messages.  ``handle_factory`` lets the CPU test-suite drive the same code over gloo with a
+numpy stand-in for the device handle (tests/fake_slab.py).
+"""
+import math
+import os
+
+import numpy
+
+KINDS = {
+    "difference_linear": 0, "difference_exponential": 1, "difference_division": 2, "difference_power": 3,
+    "maximum_linear": 4, "maximum_exponential": 5, "maximum_division": 6, "maximum_power": 7,
+}
+
+
+def slab_bounds(extent, world, rank):
+    """Planes [z0, z1) of axis 0 owned by ``rank``: as even as possible, never empty for world <= extent."""
+    return (rank * extent) // world, ((rank + 1) * extent) // world
+
+
+def _native_factory(shape, z0, z1, device):
+    from . import _lib
+    return _lib.Graph(list(shape), int(z0), int(z1), int(device))
+
+
+class SlabSolver:
+    """One rank's share of a z-slab partitioned graph cut."""
+
+    def __init__(self, shape, rank=None, world=None, device=None, handle_factory=None, group=None,
+                 passes0=1, passes_max=8):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.shape = tuple(int(s) for s in shape)
+        if len(self.shape) < 3:
+            raise ValueError("z-slab partitioning needs a lattice with at least 3 axes")
+        if self.world > self.shape[0]:
+            raise ValueError("more ranks than axis-0 planes")
+        self.z0, self.z1 = slab_bounds(self.shape[0], self.world, self.rank)
+        self.ghost_lo = self.z0 > 0
+        self.ghost_hi = self.z1 < self.shape[0]
+        self.lo_peer = self.rank - 1 if self.ghost_lo else None
+        self.hi_peer = self.rank + 1 if self.ghost_hi else None
+        self.native = handle_factory is None
+        if self.native:
+            self.device_index = torch.cuda.current_device() if device is None else int(device)
+            self.tdev = torch.device("cuda", self.device_index)
+            self.handle = _native_factory(self.shape, self.z0, self.z1, self.device_index)
+            self.handle.set_stream(torch.cuda.current_stream(self.tdev).cuda_stream)
+        else:
+            self.tdev = torch.device("cpu")
+            self.handle = handle_factory(self.shape, self.z0, self.z1)
+        self.plane = int(self.handle.slab_plane_elems())
+        # one message per direction: [labels int32 x P | pad to 8 B | flow float64 x P]
+        self.h_bytes = (self.plane * 4 + 7) // 8 * 8
+        self.msg_bytes = self.h_bytes + self.plane * 8
+        mk = lambda: torch.zeros(self.msg_bytes, dtype=torch.uint8, device=self.tdev)
+        self.send_lo, self.send_hi, self.recv_lo, self.recv_hi = mk(), mk(), mk(), mk()
+        self.passes0, self.passes_max = int(passes0), int(passes_max)
+        self.stats = {"exchanges": 0, "relabel_rounds": 0, "global_relabels": 0, "push_passes": 0}
+
+    # ---------------------------------------------------------------------------------------------- data
+    def local_slice(self, arr):
+        """The part of a global array this rank needs: its planes plus the ghost planes (1-plane overlap, so the
+        n-link stencil needs no communication)."""
+        a = self.z0 - (1 if self.ghost_lo else 0)
+        b = self.z1 + (1 if self.ghost_hi else 0)
+        return arr[a:b]
+
+    def owned_of_local(self, arr):
+        a = 1 if self.ghost_lo else 0
+        return arr[a:a + (self.z1 - self.z0)]
+
+    def reset(self):
+        self.handle.reset()
+
+    def add_regional_probability(self, prob_local, alpha, compute_f32=True):
+        self.handle.add_regional_probability(prob_local, float(alpha), bool(compute_f32))
+
+    def add_boundary(self, kind, image_local, sigma=None, spacing=False, norm=math.nan):
+        k = KINDS[kind] if isinstance(kind, str) else int(kind)
+        sp = [float(s) for s in spacing] if spacing else None
+        self.handle.add_boundary(k, image_local, 0.0 if sigma is None else float(sigma), sp, float(norm))
+
+    def add_markers(self, fg_local, bg_local):
+        self.handle.add_markers(fg_local, bg_local)
+
+    # ---------------------------------------------------------------------------------------------- messages
+    def _views(self, buf):
+        h = buf[: self.plane * 4].view(self.torch.int32)
+        f = buf[self.h_bytes:].view(self.torch.float64)
+        return h, f
+
+    def _ptr(self, t):
+        return t.data_ptr() if self.native else t
+
+    def exchange(self):
+        """pack -> send/recv with both neighbours -> unpack.  Returns 1 if a ghost label changed here."""
+        torch, dist = self.torch, self.dist
+        hl, fl = self._views(self.send_lo)
+        hh, fh = self._views(self.send_hi)
+        self.handle.slab_pack(self._ptr(hl) if self.ghost_lo else 0, self._ptr(fl) if self.ghost_lo else 0,
+                              self._ptr(hh) if self.ghost_hi else 0, self._ptr(fh) if self.ghost_hi else 0)
+        ops = []
+        if self.ghost_lo:
+            ops.append(dist.P2POp(dist.isend, self.send_lo, self.lo_peer, self.group))
+            ops.append(dist.P2POp(dist.irecv, self.recv_lo, self.lo_peer, self.group))
+        if self.ghost_hi:
+            ops.append(dist.P2POp(dist.isend, self.send_hi, self.hi_peer, self.group))
+            ops.append(dist.P2POp(dist.irecv, self.recv_hi, self.hi_peer, self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        rhl, rfl = self._views(self.recv_lo)
+        rhh, rfh = self._views(self.recv_hi)
+        changed = self.handle.slab_unpack(self._ptr(rhl) if self.ghost_lo else 0, self._ptr(rfl) if self.ghost_lo else 0,
+                                          self._ptr(rhh) if self.ghost_hi else 0, self._ptr(rfh) if self.ghost_hi else 0)
+        self.stats["exchanges"] += 1
+        return int(changed)
+
+    def _allreduce(self, value, op):
+        t = self.torch.tensor([value], dtype=self.torch.int64, device=self.tdev)
+        self.dist.all_reduce(t, op=op, group=self.group)
+        return int(t.item())
+
+    # ---------------------------------------------------------------------------------------------- solve
+    def global_relabel(self):
+        """Exact distributed backward BFS: local fixed point <-> border label exchange until nothing moves."""
+        dist = self.dist
+        self.handle.slab_relabel_begin()
+        while True:
+            self.handle.slab_relabel_relax()
+            changed = self.exchange()
+            self.stats["relabel_rounds"] += 1
+            if self.world == 1 or self._allreduce(changed, dist.ReduceOp.MAX) == 0:
+                break
+        self.stats["global_relabels"] += 1
+
+    def solve(self, max_rounds=100000):
+        """Run to a maximum preflow.  Returns this rank's energy share; use ``energy()`` for the total."""
+        dist = self.dist
+        self.handle.slab_begin()
+        passes = self.passes0
+        rounds = 0
+        while True:
+            self.global_relabel()
+            active = self._allreduce(int(self.handle.slab_count_active()), dist.ReduceOp.SUM)
+            if active == 0:
+                break
+            rounds += 1
+            if rounds > max_rounds:
+                raise RuntimeError("push-relabel did not converge within the round cap")
+            for _ in range(passes):
+                self.handle.slab_push(1)
+                self.exchange()
+                self.stats["push_passes"] += 1
+            passes = min(self.passes_max, passes * 2)
+        self.energy_part = float(self.handle.slab_finish())
+        return self.energy_part
+
+    def energy(self):
+        """Total min-cut energy (float64 all-reduce of the per-slab parts)."""
+        t = self.torch.tensor([self.energy_part], dtype=self.torch.float64, device=self.tdev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return float(t.item())
+
+    def mask(self):
+        """uint8 mask of the OWNED planes (host array)."""
+        return self.handle.get_mask()
+
+
+def graphcut_slab(fg_markers, bg_markers, image=None, boundary=None, sigma=None, spacing=False, prob=None, alpha=None,
+                  norm=math.nan, gather=True, group=None, handle_factory=None):
+    """Public multi-GPU entry point: every rank passes the SAME global arrays (host or device); each takes its
+    slab, the ranks solve one global min cut together.  Returns ``(energy, mask)``; with ``gather`` the full mask
+    is assembled on every rank (all_gather of the slabs), otherwise only the rank's own planes are returned."""
+    import torch
+    import torch.distributed as dist
+    shape = tuple(fg_markers.shape)
+    s = SlabSolver(shape, group=group, handle_factory=handle_factory)
+    if prob is not None:
+        s.add_regional_probability(s.local_slice(prob), alpha, "float32" in str(prob.dtype))
+    if boundary is not None:
+        if boundary.endswith("linear") and (isinstance(norm, float) and math.isnan(norm)):
+            raise ValueError("linear boundary terms need the GLOBAL normaliser `norm` in slab mode")
+        s.add_boundary(boundary, s.local_slice(image), sigma, spacing, norm)
+    s.add_markers(s.local_slice(fg_markers), s.local_slice(bg_markers))
+    s.solve()
+    energy = s.energy()
+    own = s.mask()
+    if not gather or s.world == 1:
+        return energy, own
+    # slabs may differ by one plane: pad to the largest, gather, trim
+    counts = [slab_bounds(shape[0], s.world, r) for r in range(s.world)]
+    pmax = max(b - a for a, b in counts)
+    dev = s.tdev
+    pad = torch.zeros((pmax,) + shape[1:], dtype=torch.uint8, device=dev)
+    pad[: own.shape[0]] = torch.from_numpy(numpy.ascontiguousarray(own)).to(dev)
+    parts = [torch.empty_like(pad) for _ in range(s.world)]
+    dist.all_gather(parts, pad, group=group)
+    full = numpy.concatenate([p[: b - a].cpu().numpy() for p, (a, b) in zip(parts, counts)], axis=0)
+    return energy, full
+
+
+# ------------------------------------------------------------------------------------------------------
+# bench support (bench.py --gpus N, launched with torchrun)
+# ------------------------------------------------------------------------------------------------------
+def bench_slab(vol, args, rank, world, local_rank):
+    """Strong-scaling run of bench.py's workload: the volume is partitioned once, the slab inputs stay resident
+    in HBM, each timed step rebuilds the terms, solves and extracts the mask.  Returns the dict bench.py prints
+    (meaningful on rank 0)."""
+    import time
+    import torch
+    import torch.distributed as dist
+    from bench import ClockSampler, measured_peak, UNIT  # noqa
+    dev = torch.device("cuda", local_rank)
+    shape = vol["shape"]
+    n = int(numpy.prod(shape))
+    s = SlabSolver(shape, rank=rank, world=world, device=local_rank)
+    d_img = torch.from_numpy(numpy.ascontiguousarray(s.local_slice(vol["image"]))).to(dev)
+    d_prob = torch.from_numpy(numpy.ascontiguousarray(s.local_slice(vol["prob"]))).to(dev)
+    d_fg = torch.from_numpy(numpy.ascontiguousarray(s.local_slice(vol["fg"])).view(numpy.uint8)).to(dev)
+    d_bg = torch.from_numpy(numpy.ascontiguousarray(s.local_slice(vol["bg"])).view(numpy.uint8)).to(dev)
+    d_mask = torch.empty((s.z1 - s.z0,) + tuple(shape[1:]), dtype=torch.uint8, device=dev)
+    launches = []
+
+    def step():
+        s.reset()
+        s.add_regional_probability(d_prob, vol["alpha"], True)
+        s.add_boundary("difference_exponential", d_img, vol["sigma"], False)
+        s.add_markers(d_fg, d_bg)
+        s.solve()
+        s.handle.get_mask_into(d_mask.data_ptr())
+        return s.energy()
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    stream = torch.cuda.current_stream()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ev0.record(stream)
+    energy = None
+    for _ in range(args.steps):
+        energy = step()
+        launches.append(s.handle.stats()["kernel_launches"])
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    fgv = torch.tensor([int(d_mask.sum().item())], dtype=torch.int64, device=dev)
+    dist.all_reduce(fgv)
+    nl = torch.tensor([int(sum(launches))], dtype=torch.int64, device=dev)
+    dist.all_reduce(nl)
+    st = s.handle.stats()
+    peak, peak_kind = measured_peak()
+
+    # ---- end to end: pinned host slabs -> device -> solve -> host mask ----
+    def pin(a):
+        t = torch.from_numpy(numpy.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+    keep = [pin(s.local_slice(vol["image"])), pin(s.local_slice(vol["prob"])),
+            pin(s.local_slice(vol["fg"]).view(numpy.uint8)), pin(s.local_slice(vol["bg"]).view(numpy.uint8))]
+    h_img, h_prob, h_fg, h_bg = (k[1] for k in keep)
+
+    def e2e_step():
+        s.reset()
+        s.add_regional_probability(h_prob, vol["alpha"], True)
+        s.add_boundary("difference_exponential", h_img, vol["sigma"], False)
+        s.add_markers(h_fg, h_bg)
+        s.solve()
+        m = s.mask()
+        return s.energy(), m
+
+    e2e_step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e_e2e, _m = e2e_step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt.item())
+    local_bytes = int(numpy.prod(h_img.shape)) * 10
+    e2e = {"value": n * args.steps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(n * 10 + (world - 1) * 2 * s.plane * 10),
+           "d2h_bytes_per_step": int(n + 8 * world), "ms_per_step": 1e3 * dt / args.steps,
+           "api": "medpy_b200.distributed.SlabSolver (reset/add_*/solve/mask) per rank", "energy_matches_resident_run": bool(e_e2e == energy),
+           "timer": "host perf_counter between barriers, max over ranks", "rank0_h2d_bytes": local_bytes}
+    push_ms, rel_ms = st["ms_push"], st["ms_relabel"]
+    roof = {"bound": "hbm", "kernel": "k_push_tile / k_relabel_tile (rank 0 totals, see share_of_step)", "achieved": None,
+            "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_kind": peak_kind,
+            "share_of_step": {"push_ms": push_ms, "relabel_ms": rel_ms, "terms_ms": st["ms_terms"], "readout_ms": st["ms_readout"],
+                              "exchanges": s.stats["exchanges"], "note": "cumulative over warm-up + timed steps on rank 0"}}
+    return {"value": n * args.steps / (ms * 1e-3) / 1e6, "ms_per_step": ms / args.steps, "clocks": clocks, "e2e": e2e,
+            "gpu_launches": int(nl.item()), "roofline": roof, "energy": energy, "fg_voxels": int(fgv.item()),
+            "push_sweeps": s.stats["push_passes"], "global_relabels": s.stats["global_relabels"],
+            "relabel_sweeps": s.stats["relabel_rounds"]}

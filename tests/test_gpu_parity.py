@@ -345,3 +345,101 @@ def test_device_resident_inputs_via_cuda_array_interface():
                                   prob=torch.from_numpy(vol["prob"]).cuda(), alpha=0.1)
     assert g1.maxflow() == g2.maxflow()
     assert numpy.array_equal(g1.get_mask(), g2.get_mask())
+
+
+# ------------------------------------------------------------------------------------------------------
+# z-slab path
+# ------------------------------------------------------------------------------------------------------
+def _two_slabs_one_gpu(vol, regional, split):
+    """Drive two slab handles that live on the SAME GPU through the mgc_slab_* protocol, moving the border messages
+    with plain device copies: exercises ghost planes, pack/unpack, the distributed relabel and the stop test
+    without needing two devices."""
+    import torch
+    from medpy_b200 import _lib
+    shape = vol["image"].shape
+    Z = shape[0]
+    bounds = [(0, split), (split, Z)]
+    hs = [_lib.Graph(list(shape), a, b, 0) for a, b in bounds]
+    P = hs[0].slab_plane_elems()
+    for (a, b), h in zip(bounds, hs):
+        lo = a - (1 if a > 0 else 0)
+        hi = b + (1 if b < Z else 0)
+        if regional:
+            h.add_regional_probability(numpy.ascontiguousarray(vol["prob"][lo:hi]), vol["alpha"], True)
+        h.add_boundary(1, numpy.ascontiguousarray(vol["image"][lo:hi]), vol["sigma"], None, float("nan"))
+        h.add_markers(numpy.ascontiguousarray(vol["fg"][lo:hi]), numpy.ascontiguousarray(vol["bg"][lo:hi]))
+        h.slab_begin()
+    mk = lambda dt: torch.zeros(P, dtype=dt, device="cuda")
+    # message buffers: rank 0's upper side <-> rank 1's lower side
+    s0h, s0f, s1h, s1f = mk(torch.int32), mk(torch.float64), mk(torch.int32), mk(torch.float64)
+
+    def exchange():
+        hs[0].slab_pack(0, 0, s0h.data_ptr(), s0f.data_ptr())
+        hs[1].slab_pack(s1h.data_ptr(), s1f.data_ptr(), 0, 0)
+        for h in hs:
+            h.synchronize()
+        c0 = hs[0].slab_unpack(0, 0, s1h.data_ptr(), s1f.data_ptr())
+        c1 = hs[1].slab_unpack(s0h.data_ptr(), s0f.data_ptr(), 0, 0)
+        return c0 or c1
+
+    passes, rounds = 1, 0
+    while True:
+        for h in hs:
+            h.slab_relabel_begin()
+        while True:
+            for h in hs:
+                h.slab_relabel_relax()
+            if not exchange():
+                break
+        if sum(h.slab_count_active() for h in hs) == 0:
+            break
+        rounds += 1
+        assert rounds < 1000
+        for _ in range(passes):
+            for h in hs:
+                h.slab_push(1)
+            exchange()
+        passes = min(8, passes * 2)
+    energy = sum(h.slab_finish() for h in hs)
+    mask = numpy.concatenate([h.get_mask() for h in hs], axis=0)
+    return energy, mask
+
+
+@pytest.mark.parametrize("shape,split,regional", [((40, 32, 32), 20, True), ((40, 32, 32), 13, False), ((37, 24, 40), 9, True)])
+def test_two_slabs_on_one_gpu_vs_oracle(shape, split, regional):
+    from medpy_b200 import synthetic
+    from oracle import energy_terms as et
+    vol = synthetic.two_blob_volume(shape, seed=4)
+    energy, mask = _two_slabs_one_gpu(vol, regional, split)
+    prob = et.build_problem(vol["fg"], vol["bg"], regional=(vol["prob"], vol["alpha"]) if regional else None,
+                            boundary=("difference_exponential", vol["image"], vol["sigma"], False))
+    oflow, omask, _ = _oracle_solve(prob)
+    assert numpy.array_equal(mask, omask)
+    assert abs(energy - oflow) <= 1e-9 * abs(oflow)
+
+
+@pytest.mark.parametrize("case", ["regional", "boundary"])
+def test_multi_gpu_nccl_slabs_vs_oracle(tmp_path, case):
+    """All visible GPUs (>= 2) solve one 48x40x40 volume together over NCCL; result must equal the oracle's."""
+    import subprocess
+    import sys
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    from medpy_b200 import synthetic
+    from oracle import energy_terms as et
+    shape = (48, 40, 40)
+    out = str(tmp_path / "r0.npz")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(ngpu, 4)),
+           "--master-addr", "127.0.0.1", "--master-port", "29617", os.path.join(root, "tests", "slab_worker.py"),
+           "x".join(map(str, shape)), case, out]
+    subprocess.run(cmd, check=True, timeout=600)
+    got = numpy.load(out)
+    vol = synthetic.two_blob_volume(shape, seed=1, with_prob=(case == "regional"))
+    prob = et.build_problem(vol["fg"], vol["bg"], regional=(vol["prob"], vol["alpha"]) if case == "regional" else None,
+                            boundary=("difference_exponential", vol["image"], vol["sigma"], False))
+    oflow, omask, _ = _oracle_solve(prob)
+    assert numpy.array_equal(got["mask"], omask)
+    assert abs(float(got["energy"]) - oflow) <= 1e-9 * abs(oflow)
