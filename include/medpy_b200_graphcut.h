@@ -23,6 +23,7 @@
 #ifndef MEDPY_B200_GRAPHCUT_H
 #define MEDPY_B200_GRAPHCUT_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -106,6 +107,11 @@ void mgc_destroy(mgc_graph* g); /* ~Graph (graph.cpp:34-43) */
 int mgc_reset(mgc_graph* g);
 const char* mgc_last_error(const mgc_graph* g); /* g may be NULL: last create() failure */
 int mgc_abi_version(void);
+/* Page-locked host buffers from a process-wide pool (the bindings hand the mask back in one: a device->host copy
+ * into pinned memory runs at PCIe rate, into fresh pageable memory at a fraction of it).  mgc_host_free returns
+ * the block to the pool. */
+int mgc_host_alloc(size_t bytes, void** out);
+void mgc_host_free(void* p);
 /* Use an externally owned cudaStream_t (e.g. torch's current stream) for all work of this handle. */
 int mgc_set_stream(mgc_graph* g, void* cuda_stream);
 int mgc_synchronize(mgc_graph* g);

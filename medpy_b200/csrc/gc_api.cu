@@ -57,6 +57,23 @@ void pool_free(int dev, size_t bytes, void* p)
     g_pool[{dev, round_up(bytes)}].push_back(p);
 }
 
+// pinned host blocks (mask read-back buffers handed to the binding): same pooling idea as device memory
+std::map<size_t, std::vector<void*>> g_host_pool;
+std::map<void*, size_t> g_host_live;
+
+int cached_sm_count(int dev)
+{
+    static std::mutex mu;
+    static std::map<int, int> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(dev);
+    if (it != cache.end()) return it->second;
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev] = n;
+    return n;
+}
+
 struct Buf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -102,6 +119,14 @@ struct mgc_graph {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaEvent_t ev[6] = {};
+    // host -> device staging runs on its own stream so that the copy of the next term overlaps the kernel of the
+    // previous one; the host only waits for the COPY (its pointer is borrowed for the call), never for the kernel
+    cudaStream_t up_stream = nullptr;
+    cudaEvent_t ev_up = nullptr;
+    cudaEvent_t ev_slot[4] = {};       // main-stream point after which a staging slot may be overwritten
+    bool slot_used[4] = {false, false, false, false};
+    cudaEvent_t ev_terms[2] = {};      // span of the term kernels since the last reset
+    bool terms_open = false;
 
     bool caps_fresh = true;            // capacity arrays not written yet since create/reset (hold garbage)
     bool tr_fresh = true;              // same for tr[]
@@ -154,6 +179,8 @@ namespace {
     } while (0)
 
 inline unsigned nblocks(const mgc_graph* g) { return (g->L.n + 255u) / 256u; }
+// grid of the grid-stride reduction kernels (partials per launch)
+inline unsigned rblocks(const mgc_graph* g) { const unsigned nb = nblocks(g); return nb < REDUCE_BLOCKS ? nb : REDUCE_BLOCKS; }
 
 int alloc_buf(mgc_graph* g, size_t bytes, void** out)
 {
@@ -194,6 +221,24 @@ int gather_launch(mgc_graph* g, const char* src, const Strides4& st, E* dst)
     return MGC_OK;
 }
 
+// host -> device copy on the upload stream: waits until the staging slot's previous reader is done, makes the
+// main stream wait for the copy, and blocks the HOST only until the copy itself has finished.
+int upload(mgc_graph* g, void* dst, const void* src, size_t bytes, int slot)
+{
+    if (g->slot_used[slot]) CK(cudaStreamWaitEvent(g->up_stream, g->ev_slot[slot], 0));
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g->up_stream));
+    CK(cudaEventRecord(g->ev_up, g->up_stream));
+    CK(cudaStreamWaitEvent(g->stream, g->ev_up, 0));
+    CK(cudaEventSynchronize(g->ev_up));
+    return MGC_OK;
+}
+
+// call after the kernel(s) that read the staging slots have been launched
+void slots_release(mgc_graph* g)
+{
+    for (int i = 0; i < 4; ++i) { cudaEventRecord(g->ev_slot[i], g->stream); g->slot_used[i] = true; }
+}
+
 int stage_input(mgc_graph* g, const mgc_array* a, int slot, const void** out)
 {
     const size_t es = dtype_size(a->dtype);
@@ -223,7 +268,8 @@ int stage_input(mgc_graph* g, const mgc_array* a, int slot, const void** out)
     int rc = ensure_scratch(g, g->scratch[slot], bytes);
     if (rc) return rc;
     if (contiguous) {
-        CK(cudaMemcpyAsync(g->scratch[slot].p, a->data, bytes, cudaMemcpyHostToDevice, g->stream));
+        rc = upload(g, g->scratch[slot].p, a->data, bytes, slot);
+        if (rc) return rc;
         *out = g->scratch[slot].p;
         return MGC_OK;
     }
@@ -231,9 +277,11 @@ int stage_input(mgc_graph* g, const mgc_array* a, int slot, const void** out)
     if (a->mem == MGC_MEM_HOST) {
         rc = ensure_scratch(g, g->raw, (size_t)span);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(g->raw.p, a->data, (size_t)span, cudaMemcpyHostToDevice, g->stream));
+        rc = upload(g, g->raw.p, a->data, (size_t)span, 3);
+        if (rc) return rc;
         src = (const char*)g->raw.p;
     }
+    else if (g->slot_used[slot]) CK(cudaStreamWaitEvent(g->stream, g->ev_slot[slot], 0));
     switch (a->dtype) {
         case MGC_F32: gather_launch<float>(g, src, st, (float*)g->scratch[slot].p); break;
         case MGC_F64: gather_launch<double>(g, src, st, (double*)g->scratch[slot].p); break;
@@ -248,7 +296,7 @@ int stage_input(mgc_graph* g, const mgc_array* a, int slot, const void** out)
 
 int finish_flow_const(mgc_graph* g)
 {
-    k_sum_partials<<<1, 256, 0, g->stream>>>(g->partials, nblocks(g), g->d_scalars);
+    k_sum_partials<<<1, 256, 0, g->stream>>>(g->partials, rblocks(g), g->d_scalars);
     g->st.kernel_launches++;
     CK(cudaGetLastError());
     return MGC_OK;
@@ -274,6 +322,27 @@ struct Timer {
         *acc += ms;
     }
 };
+
+// term kernels are not synchronised one by one: their span on the stream is measured between the first term after a
+// reset and the last term before the solve, and read when the solve synchronises anyway
+struct TermSpan {
+    mgc_graph* g;
+    explicit TermSpan(mgc_graph* g_) : g(g_)
+    {
+        if (!g->terms_open) { cudaEventRecord(g->ev_terms[0], g->stream); g->terms_open = true; }
+    }
+    void stop() { slots_release(g); cudaEventRecord(g->ev_terms[1], g->stream); }
+};
+
+void resolve_term_span(mgc_graph* g)
+{
+    if (!g->terms_open) return;
+    if (cudaEventSynchronize(g->ev_terms[1]) == cudaSuccess) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, g->ev_terms[0], g->ev_terms[1]) == cudaSuccess) g->st.ms_terms += ms;
+    }
+    g->terms_open = false;
+}
 
 int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool slab, int32_t device, mgc_graph** out)
 {
@@ -320,6 +389,11 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
     unsigned s = (unsigned)n;
     for (int d = 0; d < 4; ++d) { g->L.dim[d] = 1; g->L.stride[d] = 1; }
     for (int d = 0; d < g->nd; ++d) { g->L.dim[d] = (int)dims[d]; s /= (unsigned)dims[d]; g->L.stride[d] = s; }
+    for (int d = 0; d < 4; ++d) {
+        const unsigned long long st = g->L.stride[d];
+        // ceil(2^64 / st) = floor((2^64 - 1) / st) + 1 for st > 1 that does not divide 2^64 ... and also when it does
+        g->L.magic[d] = st <= 1 ? 0ull : (~0ull / st) + 1ull;
+    }
     g->L.n = (unsigned)n;
     g->L.plane = g->L.stride[0];
     g->L.own0 = own0; g->L.own1 = own1;
@@ -349,11 +423,7 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
         for (int i = 0; i < 2 && !rc; ++i) { rc = alloc_buf(g, tb, &p); g->rl_items[i] = (int*)p; }
         for (int i = 0; i < 4 && !rc; ++i) { rc = alloc_buf(g, tb, &p); g->pl_items[i >> 1][i & 1] = (int*)p; }
         if (!rc) { rc = alloc_buf(g, 64, &p); g->d_tcount = (int*)p; }
-        {
-            cudaDeviceProp prop{};
-            if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0)
-                g->n_ctas = 2 * prop.multiProcessorCount;   // k_push_tile is built for 2 CTAs per SM
-        }
+        g->n_ctas = 2 * cached_sm_count(device);   // k_push_tile is built for 2 CTAs per SM
         g->use_tiles = true;
         if (const char* sv = getenv("MEDPY_GC_SOLVER")) if (!strcmp(sv, "v0")) g->use_tiles = false;
         if (const char* e1 = getenv("MEDPY_GC_ITERS")) if (atoi(e1) > 0) g->tile_iters = atoi(e1);
@@ -364,6 +434,10 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
     if (cudaStreamCreate(&g->stream) != cudaSuccess) { g_create_error = "cudaStreamCreate failed"; mgc_destroy(g); return MGC_E_CUDA; }
     g->own_stream = true;
     for (auto& ev : g->ev) cudaEventCreate(&ev);
+    cudaStreamCreateWithFlags(&g->up_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&g->ev_up, cudaEventDisableTiming);
+    for (auto& ev : g->ev_slot) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for (auto& ev : g->ev_terms) cudaEventCreate(&ev);
     if (const char* s1 = getenv("MEDPY_GC_SWEEPS")) g->sweeps_per_round = atoi(s1) > 0 ? atoi(s1) : g->sweeps_per_round;
     if (const char* s2 = getenv("MEDPY_GC_RELAX_BATCH")) g->relax_batch = atoi(s2) > 0 ? atoi(s2) : g->relax_batch;
     g->st.n_voxels = (int64_t)n;
@@ -530,7 +604,13 @@ int relabel_tiles_begin(mgc_graph* g)
 {
     if (g->labels_fresh) { g->labels_fresh = false; g->rl_cur = 0; return MGC_OK; }
     CK(cudaMemsetAsync(g->d_tcount, 0, 2 * sizeof(int), g->stream));
-    k_relabel_reset<<<g->TL.ntiles, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S.rmask, g->S.height, g->rflag, rl(g, 0));
+    CK(cudaMemsetAsync(g->rflag, 0, (size_t)g->TL.ntiles * sizeof(int), g->stream));
+    {
+        const unsigned nruns = (unsigned)g->L.dim[0] * (unsigned)g->L.dim[1] * (unsigned)g->TL.nt[2];
+        unsigned grid = (nruns + 255u) / 256u;
+        if (grid > (unsigned)g->n_ctas * 8u) grid = (unsigned)g->n_ctas * 8u;
+        k_relabel_reset<<<grid, 256, 0, g->stream>>>(g->L, g->TL, g->S.rmask, g->S.height, g->rflag, rl(g, 0));
+    }
     g->st.kernel_launches++;
     g->rl_cur = 0;
     CK(cudaGetLastError());
@@ -649,11 +729,10 @@ int solve_tiles(mgc_graph* g)
 
 int readout(mgc_graph* g, double* energy_part)
 {
-    k_mask<<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S.height, g->mask_dev);
-    k_absorbed<double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, g->partials);
+    k_readout<double><<<rblocks(g), 256, 0, g->stream>>>(g->L, g->S, g->mask_dev, g->partials);
     CK(cudaMemsetAsync(g->d_scalars + 1, 0, sizeof(double), g->stream));
-    k_sum_partials<<<1, 256, 0, g->stream>>>(g->partials, nblocks(g), g->d_scalars + 1);
-    g->st.kernel_launches += 3;
+    k_sum_partials<<<1, 256, 0, g->stream>>>(g->partials, rblocks(g), g->d_scalars + 1);
+    g->st.kernel_launches += 2;
     double sc[2] = {0, 0};
     CK(cudaMemcpyAsync(sc, g->d_scalars, sizeof(sc), cudaMemcpyDeviceToHost, g->stream));
     CK(cudaStreamSynchronize(g->stream));
@@ -693,6 +772,10 @@ void mgc_destroy(mgc_graph* g)
     for (auto& b : g->scratch) if (b.p) pool_free(g->device, b.bytes, b.p);
     if (g->raw.p) pool_free(g->device, g->raw.bytes, g->raw.p);
     for (auto& ev : g->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : g->ev_slot) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : g->ev_terms) if (ev) cudaEventDestroy(ev);
+    if (g->ev_up) cudaEventDestroy(g->ev_up);
+    if (g->up_stream) { cudaStreamSynchronize(g->up_stream); cudaStreamDestroy(g->up_stream); }
     if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
     delete g;
 }
@@ -712,7 +795,32 @@ int mgc_reset(mgc_graph* g)
     int64_t n = g->st.n_voxels;
     g->st = mgc_stats{};
     g->st.n_voxels = n;
+    g->terms_open = false;
     return MGC_OK;
+}
+
+int mgc_host_alloc(size_t bytes, void** out)
+{
+    if (!out || !bytes) return MGC_E_ARG;
+    const size_t rb = round_up(bytes);
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto it = g_host_pool.find(rb);
+    void* p = nullptr;
+    if (it != g_host_pool.end() && !it->second.empty()) { p = it->second.back(); it->second.pop_back(); }
+    else if (cudaHostAlloc(&p, rb, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); g_create_error = "pinned host allocation failed"; return MGC_E_NOMEM; }
+    g_host_live[p] = rb;
+    *out = p;
+    return MGC_OK;
+}
+
+void mgc_host_free(void* p)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto it = g_host_live.find(p);
+    if (it == g_host_live.end()) return;
+    g_host_pool[it->second].push_back(p);
+    g_host_live.erase(it);
 }
 
 int mgc_set_stream(mgc_graph* g, void* cuda_stream)
@@ -737,21 +845,21 @@ int mgc_add_regional_probability(mgc_graph* g, const mgc_array* prob, double alp
     if (prob->dtype != MGC_F32 && prob->dtype != MGC_F64) FAIL(MGC_E_ARG, "probability map must be float32 or float64");
     if (compute_dtype != MGC_F32 && compute_dtype != MGC_F64) FAIL(MGC_E_ARG, "compute dtype must be float32 or float64");
     CK(cudaSetDevice(g->device));
-    Timer t(g, &g->st.ms_terms);
+    TermSpan t(g);
     const void* p = nullptr;
     int rc = stage_input(g, prob, 0, &p);
     if (rc) return rc;
     if (prob->dtype == MGC_F32)
-        k_regional<float, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const float*)p, alpha, compute_dtype == MGC_F32, g->tr_fresh ? 1 : 0, g->partials);
+        k_regional<float, double><<<rblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const float*)p, alpha, compute_dtype == MGC_F32, g->tr_fresh ? 1 : 0, g->partials);
     else
-        k_regional<double, double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const double*)p, alpha, 0, g->tr_fresh ? 1 : 0, g->partials);
+        k_regional<double, double><<<rblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const double*)p, alpha, 0, g->tr_fresh ? 1 : 0, g->partials);
     g->tr_fresh = false;
     g->st.kernel_launches++;
     CK(cudaGetLastError());
     rc = finish_flow_const(g);
     if (rc) return rc;
     invalidate(g);
-    t.stop_sync();
+    t.stop();
     return MGC_OK;
 }
 
@@ -760,20 +868,20 @@ int mgc_add_tweights_dense(mgc_graph* g, const mgc_array* src, const mgc_array* 
     if (!g || !src || !snk) return MGC_E_ARG;
     if (src->dtype != MGC_F64 || snk->dtype != MGC_F64) FAIL(MGC_E_ARG, "dense t-weights must be float64");
     CK(cudaSetDevice(g->device));
-    Timer t(g, &g->st.ms_terms);
+    TermSpan t(g);
     const void *ps = nullptr, *pk = nullptr;
     int rc = stage_input(g, src, 0, &ps);
     if (rc) return rc;
     rc = stage_input(g, snk, 1, &pk);
     if (rc) return rc;
-    k_tweights_dense<double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const double*)ps, (const double*)pk, g->tr_fresh ? 1 : 0, g->partials);
+    k_tweights_dense<double><<<rblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const double*)ps, (const double*)pk, g->tr_fresh ? 1 : 0, g->partials);
     g->tr_fresh = false;
     g->st.kernel_launches++;
     CK(cudaGetLastError());
     rc = finish_flow_const(g);
     if (rc) return rc;
     invalidate(g);
-    t.stop_sync();
+    t.stop();
     return MGC_OK;
 }
 
@@ -783,19 +891,19 @@ int mgc_add_markers(mgc_graph* g, const mgc_array* fg, const mgc_array* bg)
     if (!fg && !bg) return MGC_OK;
     if ((fg && fg->dtype != MGC_U8) || (bg && bg->dtype != MGC_U8)) FAIL(MGC_E_ARG, "markers must be uint8 / bool");
     CK(cudaSetDevice(g->device));
-    Timer t(g, &g->st.ms_terms);
+    TermSpan t(g);
     const void *pf = nullptr, *pb = nullptr;
     int rc = MGC_OK;
     if (fg) { rc = stage_input(g, fg, 0, &pf); if (rc) return rc; }
     if (bg) { rc = stage_input(g, bg, 1, &pb); if (rc) return rc; }
-    k_markers<double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const uint8_t*)pf, (const uint8_t*)pb, g->tr_fresh ? 1 : 0, g->partials);
+    k_markers<double><<<rblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const uint8_t*)pf, (const uint8_t*)pb, g->tr_fresh ? 1 : 0, g->partials);
     g->tr_fresh = false;
     g->st.kernel_launches++;
     CK(cudaGetLastError());
     rc = finish_flow_const(g);
     if (rc) return rc;
     invalidate(g);
-    t.stop_sync();
+    t.stop();
     return MGC_OK;
 }
 
@@ -804,7 +912,7 @@ int mgc_add_boundary(mgc_graph* g, int32_t kind, const mgc_array* image, double 
     if (!g || !image) return MGC_E_ARG;
     if (kind < 0 || kind > 7) FAIL(MGC_E_ARG, "unknown boundary term");
     CK(cudaSetDevice(g->device));
-    Timer t(g, &g->st.ms_terms);
+    TermSpan t(g);
     const void* img = nullptr;
     int rc = stage_input(g, image, 2, &img);
     if (rc) return rc;
@@ -845,7 +953,8 @@ int mgc_add_boundary(mgc_graph* g, int32_t kind, const mgc_array* image, double 
     CK(cudaGetLastError());
     int bad = 0;
     CK(cudaMemcpyAsync(&bad, g->d_flags, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
-    t.stop_sync();
+    t.stop();
+    CK(cudaStreamSynchronize(g->stream));      // the weight check must be reported by this call (ValueError)
     { float ms = 0; cudaEventElapsedTime(&ms, g->ev[2], g->ev[3]); g->st.ms_boundary = ms; }
     invalidate(g);
     g->has_nlinks = true;
@@ -859,7 +968,7 @@ int mgc_add_nweights_dense(mgc_graph* g, int32_t axis, const mgc_array* fwd, con
     if (axis < 0 || axis >= g->user_ndim) FAIL(MGC_E_ARG, "bad axis");
     if (fwd->dtype != MGC_F64 || bwd->dtype != MGC_F64) FAIL(MGC_E_ARG, "dense n-weights must be float64");
     CK(cudaSetDevice(g->device));
-    Timer t(g, &g->st.ms_terms);
+    TermSpan t(g);
     const void *pf = nullptr, *pb = nullptr;
     int rc = stage_input(g, fwd, 0, &pf);
     if (rc) return rc;
@@ -878,7 +987,8 @@ int mgc_add_nweights_dense(mgc_graph* g, int32_t axis, const mgc_array* fwd, con
     CK(cudaGetLastError());
     int bad = 0;
     CK(cudaMemcpyAsync(&bad, g->d_flags, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
-    t.stop_sync();
+    t.stop();
+    CK(cudaStreamSynchronize(g->stream));
     invalidate(g);
     g->has_nlinks = true;
     if (bad) FAIL(MGC_E_WEIGHT, "Negative or zero weights are not allowed.");
@@ -891,6 +1001,7 @@ int mgc_maxflow(mgc_graph* g, double* energy)
     if (g->slab) FAIL(MGC_E_STATE, "z-slab handles are stepped with mgc_slab_*");
     CK(cudaSetDevice(g->device));
     if (g->solved) { if (energy) *energy = g->energy; return MGC_OK; }
+    resolve_term_span(g);
     {
         Timer t(g, &g->st.ms_solve);
         int rc = MGC_OK;
@@ -1053,6 +1164,7 @@ int mgc_slab_begin(mgc_graph* g)
 {
     if (!g) return MGC_E_ARG;
     CK(cudaSetDevice(g->device));
+    resolve_term_span(g);
     if (g->use_tiles) {
         int rc = materialise_zeros(g);
         if (rc) return rc;

@@ -19,6 +19,7 @@ struct Lattice {
     int nd;                 // canonical number of axes: 3 or 4
     int dim[4];             // extents, axis 0 slowest
     unsigned stride[4];     // element strides (C order)
+    unsigned long long magic[4];  // ceil(2^64 / stride[d]) (0 when stride[d] == 1): exact u32 division by multiply-high
     unsigned n;             // voxels in the local lattice (< 2^31)
     unsigned plane;         // voxels per axis-0 plane
     int own0, own1;         // owned axis-0 planes [own0, own1): all of them unless this is a z-slab
@@ -34,13 +35,20 @@ struct State {
     uint8_t* rmask;
 };
 
+// floor(v / stride[d]) for v < 2^32 without a hardware divide: v * ceil(2^64/d) >> 64 is exact for 32-bit v
+__device__ __forceinline__ unsigned div_stride(const Lattice& L, unsigned v, int d)
+{
+    const unsigned long long m = L.magic[d];
+    return m ? (unsigned)__umul64hi((unsigned long long)v, m) : v;
+}
+
 template <int ND>
 __device__ __forceinline__ void decode(const Lattice& L, unsigned v, int (&c)[ND])
 {
     unsigned r = v;
 #pragma unroll
     for (int d = 0; d < ND - 1; ++d) {
-        unsigned q = r / L.stride[d];
+        unsigned q = div_stride(L, r, d);
         c[d] = (int)q;
         r -= q * L.stride[d];
     }
@@ -56,6 +64,6 @@ __device__ __forceinline__ int dir_offset(const Lattice& L, int k)
 
 __device__ __forceinline__ bool owned(const Lattice& L, unsigned v)
 {
-    int p = (int)(v / L.plane);
+    int p = (int)div_stride(L, v, 0);   // plane == stride[0]
     return p >= L.own0 && p < L.own1;
 }

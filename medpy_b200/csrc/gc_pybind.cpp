@@ -168,11 +168,16 @@ public:
     {
         std::vector<py::ssize_t> shp(shape_.begin(), shape_.end());
         if (owned_planes_ >= 0) shp[0] = owned_planes_;
-        py::array_t<uint8_t> out(shp);
+        size_t n = 1;
+        for (auto d : shp) n *= (size_t)d;
+        // pinned, pooled destination: the numpy array owns it through a capsule that returns it to the pool
+        void* mem = nullptr;
+        if (mgc_host_alloc(n ? n : 1, &mem) != MGC_OK) throw std::runtime_error("pinned host allocation failed");
+        py::capsule owner(mem, [](void* p) { mgc_host_free(p); });
         int rc;
-        { uint8_t* p = out.mutable_data(); py::gil_scoped_release rel; rc = mgc_get_mask(g_, p, MGC_MEM_HOST); }
+        { py::gil_scoped_release rel; rc = mgc_get_mask(g_, (uint8_t*)mem, MGC_MEM_HOST); }
         check(rc, g_);
-        return out;
+        return py::array_t<uint8_t>(shp, (const uint8_t*)mem, owner);
     }
     void get_mask_into(uintptr_t device_ptr)
     {

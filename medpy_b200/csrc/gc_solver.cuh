@@ -152,32 +152,29 @@ __global__ void __launch_bounds__(256) k_count_active(Lattice L, State<T> S, uns
 // ---------------------------------------------------------------------------------------------------
 // read-out: mask (K5) and energy (K6)
 // ---------------------------------------------------------------------------------------------------
-// mask[v] = 1 unless v can reach the sink (bin/medpy_graphcut_voxel.py:177-181 with graph.h:560-571)
-__global__ void __launch_bounds__(256) k_mask(Lattice L, const int* __restrict__ height, uint8_t* __restrict__ mask)
-{
-    unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= L.n) return;
-    mask[v] = height[v] >= MGC_HINF ? 1 : 0;
-}
-
-// flow absorbed by the sink links of the owned voxels; deterministic
+// mask[v] = 1 unless v can reach the sink (bin/medpy_graphcut_voxel.py:177-181 with graph.h:560-571), fused with the
+// energy reduction: flow absorbed by the sink links of the owned voxels (fixed-order fp64 sums, deterministic)
 template <typename T>
-__global__ void __launch_bounds__(256) k_absorbed(Lattice L, State<T> S, double* __restrict__ partials)
+__global__ void __launch_bounds__(256) k_readout(Lattice L, State<T> S, uint8_t* __restrict__ mask, double* __restrict__ partials)
 {
-    __shared__ double sh[256];
-    unsigned tid = threadIdx.x;
-    unsigned v = blockIdx.x * blockDim.x + tid;
+    __shared__ double sh[8];
     double a = 0.0;
-    if (v < L.n && owned(L, v)) {
-        a = (double)S.sink[v];
+    const unsigned step = gridDim.x * blockDim.x;
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < L.n; v += step) {
+        mask[v] = S.height[v] >= MGC_HINF ? 1 : 0;
+        if (owned(L, v)) a = __dadd_rn(a, (double)S.sink[v]);
     }
-    sh[tid] = a;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a = __dadd_rn(a, __shfl_down_sync(0xffffffffu, a, o));
+    const unsigned tid = threadIdx.x;
+    if ((tid & 31) == 0) sh[tid >> 5] = a;
     __syncthreads();
-    for (unsigned s = 128; s > 0; s >>= 1) {
-        if (tid < s) sh[tid] = __dadd_rn(sh[tid], sh[tid + s]);
-        __syncthreads();
+    if (tid == 0) {
+        double t = sh[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) t = __dadd_rn(t, sh[w]);
+        partials[blockIdx.x] = t;
     }
-    if (tid == 0) partials[blockIdx.x] = sh[0];
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -211,17 +211,24 @@ __device__ __forceinline__ double add_tweights_dev(T& tr, double s, double t)
     return (s < t) ? s : t;
 }
 
+// Deterministic reduction: every thread accumulates its own grid-stride share in a fixed order, then warp
+// shuffles + one shared-memory step give the block's partial; k_sum_partials adds the (<= REDUCE_BLOCKS) partials
+// in a fixed order.  The result depends only on the launch shape, which is fixed per lattice size.
+#define REDUCE_BLOCKS 1184   // 8 x 148 SMs
 __device__ __forceinline__ void block_sum_store(double x, double* __restrict__ partials)
 {
-    __shared__ double sh[256];
-    unsigned tid = threadIdx.x;
-    sh[tid] = x;
+    __shared__ double sh[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = __dadd_rn(x, __shfl_down_sync(0xffffffffu, x, o));
+    const unsigned tid = threadIdx.x;
+    if ((tid & 31) == 0) sh[tid >> 5] = x;
     __syncthreads();
-    for (unsigned s = 128; s > 0; s >>= 1) {
-        if (tid < s) sh[tid] = __dadd_rn(sh[tid], sh[tid + s]);
-        __syncthreads();
+    if (tid == 0) {
+        double t = sh[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) t = __dadd_rn(t, sh[w]);
+        partials[blockIdx.x] = t;
     }
-    if (tid == 0) partials[blockIdx.x] = sh[0];
 }
 
 // regional_probability_map (energy_voxel.py:62-65): products formed in the map's dtype when F32 != 0
@@ -229,9 +236,9 @@ template <typename E, typename T>
 __global__ void __launch_bounds__(256)
 k_regional(Lattice L, State<T> S, const E* __restrict__ prob, double alpha, int compute_f32, int fresh, double* __restrict__ partials)
 {
-    unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
     double m = 0.0;
-    if (v < L.n) {
+    const unsigned step = gridDim.x * blockDim.x;
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < L.n; v += step) {
         double s, t;
         if (compute_f32) {
             float p = (float)prob[v];
@@ -246,7 +253,7 @@ k_regional(Lattice L, State<T> S, const E* __restrict__ prob, double alpha, int 
         T tr = fresh ? (T)0 : S.tr[v];      // fresh: tr[] holds garbage (first t-link term after create/reset)
         double mm = add_tweights_dev(tr, s, t);
         S.tr[v] = tr;
-        if (owned(L, v)) m = mm;
+        if (owned(L, v)) m = __dadd_rn(m, mm);
     }
     block_sum_store(m, partials);
 }
@@ -256,13 +263,13 @@ __global__ void __launch_bounds__(256)
 k_tweights_dense(Lattice L, State<T> S, const double* __restrict__ src, const double* __restrict__ snk,
                  int fresh, double* __restrict__ partials)
 {
-    unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
     double m = 0.0;
-    if (v < L.n) {
+    const unsigned step = gridDim.x * blockDim.x;
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < L.n; v += step) {
         T tr = fresh ? (T)0 : S.tr[v];
         double mm = add_tweights_dev(tr, src[v], snk[v]);
         S.tr[v] = tr;
-        if (owned(L, v)) m = mm;
+        if (owned(L, v)) m = __dadd_rn(m, mm);
     }
     block_sum_store(m, partials);
 }
@@ -273,9 +280,9 @@ __global__ void __launch_bounds__(256)
 k_markers(Lattice L, State<T> S, const uint8_t* __restrict__ fg, const uint8_t* __restrict__ bg,
           int fresh, double* __restrict__ partials)
 {
-    unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
     double m = 0.0;
-    if (v < L.n) {
+    const unsigned step = gridDim.x * blockDim.x;
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < L.n; v += step) {
         bool f = fg && fg[v], b = bg && bg[v];
         if (f || b || fresh) {
             T tr = fresh ? (T)0 : S.tr[v];
@@ -283,7 +290,7 @@ k_markers(Lattice L, State<T> S, const uint8_t* __restrict__ fg, const uint8_t* 
             if (f) mm = add_tweights_dev(tr, 65535.0, 0.0);
             if (b) mm = __dadd_rn(mm, add_tweights_dev(tr, 0.0, 65535.0));
             S.tr[v] = tr;
-            if (owned(L, v)) m = mm;
+            if (owned(L, v)) m = __dadd_rn(m, mm);
         }
     }
     block_sum_store(m, partials);

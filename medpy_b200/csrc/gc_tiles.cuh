@@ -178,22 +178,43 @@ __global__ void __launch_bounds__(TILE_VOX) k_init_tile(Lattice L, Tiles TL, Sta
     }
 }
 
-// later global relabels: labels from the (incrementally maintained) residual mask; 5 B/voxel
-__global__ void __launch_bounds__(TILE_VOX) k_relabel_reset(Lattice L, Tiles TL, const uint8_t* __restrict__ rmask,
-                                                            int* __restrict__ height, int* __restrict__ rflag, WorkList rl)
+// later global relabels: labels from the (incrementally maintained) residual mask; 1 B read + 4 B written per voxel.
+// One thread per 8-voxel x-run of a tile row, consecutive threads on consecutive runs (coalesced); rflag must be
+// zero on entry (the host memsets it): a run that holds an unlabelled voxel with residual out-arcs lists its tile.
+__global__ void __launch_bounds__(256) k_relabel_reset(Lattice L, Tiles TL, const uint8_t* __restrict__ rmask,
+                                                       int* __restrict__ height, int* __restrict__ rflag, WorkList rl)
 {
-    const TileCtx c = tile_ctx(L, TL, blockIdx.x);
-    int needs = 0;
-    if (c.inb) {
-        const unsigned m = rmask[c.v];
-        const int h = (c.own && (m & RM_SINK)) ? 1 : MGC_HINF;
-        height[c.v] = h;
-        needs = (c.own && (m & 0x3fu) != 0 && h == MGC_HINF) ? 1 : 0;
-    }
-    const int any_needs = __syncthreads_or(needs);
-    if (threadIdx.x == 0) {
-        rflag[c.t] = any_needs;
-        if (any_needs) rl.items[atomicAdd(rl.count, 1)] = c.t;
+    const unsigned ntx = (unsigned)TL.nt[2];
+    const unsigned nruns = (unsigned)L.dim[0] * (unsigned)L.dim[1] * ntx;
+    for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < nruns; r += gridDim.x * blockDim.x) {
+        const unsigned tx = r % ntx, zy = r / ntx;
+        const unsigned gy = zy % (unsigned)L.dim[1], gz = zy / (unsigned)L.dim[1];
+        const unsigned x0 = tx * TILE;
+        const int nx = (int)min((unsigned)TILE, (unsigned)L.dim[2] - x0);
+        const unsigned base = gz * L.stride[0] + gy * L.stride[1] + x0;
+        const bool own = (int)gz >= L.own0 && (int)gz < L.own1;
+        int needs = 0;
+        if (nx == TILE && (base & 7u) == 0u) {
+            const uint2 m8 = *reinterpret_cast<const uint2*>(rmask + base);
+            int h[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const unsigned m = ((i < 4 ? m8.x : m8.y) >> (8 * (i & 3))) & 0xffu;
+                h[i] = (own && (m & RM_SINK)) ? 1 : MGC_HINF;
+                needs |= (own && (m & 0x3fu) != 0 && h[i] == MGC_HINF) ? 1 : 0;
+            }
+            int4* dst = reinterpret_cast<int4*>(height + base);
+            dst[0] = make_int4(h[0], h[1], h[2], h[3]);
+            dst[1] = make_int4(h[4], h[5], h[6], h[7]);
+        } else {
+            for (int i = 0; i < nx; ++i) {
+                const unsigned m = rmask[base + i];
+                const int h = (own && (m & RM_SINK)) ? 1 : MGC_HINF;
+                height[base + i] = h;
+                needs |= (own && (m & 0x3fu) != 0 && h == MGC_HINF) ? 1 : 0;
+            }
+        }
+        if (needs) list_push(rflag, rl, (int)(((gz >> 3) * (unsigned)TL.nt[1] + (gy >> 3)) * ntx + tx));
     }
 }
 

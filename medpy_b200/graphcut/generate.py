@@ -73,10 +73,8 @@ def graph_from_voxels(fg_markers, bg_markers, regional_term=False, boundary_term
     _logger.info("Setting terminal weights for the markers...")
     if bg.shape != fg.shape:
         raise ValueError("fg_markers and bg_markers must have the same shape")
-    has_fg = bool(fg.any())
-    has_bg = bool(bg.any())
-    if has_fg or has_bg:
-        # set_source_nodes(fg ids) THEN set_sink_nodes(bg ids) (generate.py:169-172) as one fused device pass
-        graph._add_markers(fg if has_fg else None, bg if has_bg else None)
+    # set_source_nodes(fg ids) THEN set_sink_nodes(bg ids) (generate.py:169-172) as one fused device pass.  The
+    # reference skips an empty marker set; an all-False array does the same thing here, so no host-side scan.
+    graph._add_markers(fg, bg)
 
     return graph.get_graph()
