@@ -195,15 +195,16 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     size = args.size
-    vol = make_volume(size)
-    shape = vol["shape"]
+    shape = (size, size, size)
     n = int(numpy.prod(shape))
     peak, peak_kind = measured_peak()
 
     if world > 1:
         from medpy_b200 import distributed as mdist
-        result = mdist.bench_slab(vol, args, rank, world, local_rank)
+        result = mdist.bench_slab(shape, args, rank, world, local_rank)   # each rank builds only its own planes
+        vol = {"sigma": result["sigma"]}
     else:
+        vol = make_volume(size)
         result = bench_single(vol, args, torch)
 
     if rank != 0:

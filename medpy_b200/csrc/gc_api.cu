@@ -6,6 +6,7 @@
 #include "gc_terms.cuh"
 #include "gc_solver.cuh"
 #include "gc_tiles.cuh"
+#include "gc_persist.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -149,6 +150,9 @@ struct mgc_graph {
     int rl_cur = 0;                    // relabel list consumed next
     bool labels_fresh = false;         // labels + relabel list 0 come straight from k_init_tile
     int n_ctas = 296;                  // persistent CTAs per tile-kernel launch
+    bool use_coop = false;             // whole solve as one cooperative launch (gc_persist.cuh); opt-in, MEDPY_GC_COOP=1
+    int coop_bfs_grid = 0;             // co-resident CTAs of k_bfs_coop (0: per-pass host loop)
+    int coop_grid = 0;                 // co-resident CTAs of k_solve_coop
     int tile_iters = 8;                // synchronous push/relabel rounds per tile visit
     int passes0 = 1, passes_max = 8;   // two-colour passes per round: starts at passes0, doubles up to passes_max
 
@@ -422,13 +426,35 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
         if (!rc) { rc = alloc_buf(g, tb, &p); g->rflag = (int*)p; }
         for (int i = 0; i < 2 && !rc; ++i) { rc = alloc_buf(g, tb, &p); g->rl_items[i] = (int*)p; }
         for (int i = 0; i < 4 && !rc; ++i) { rc = alloc_buf(g, tb, &p); g->pl_items[i >> 1][i & 1] = (int*)p; }
-        if (!rc) { rc = alloc_buf(g, 64, &p); g->d_tcount = (int*)p; }
+        if (!rc) { rc = alloc_buf(g, 256, &p); g->d_tcount = (int*)p; }
         g->n_ctas = 2 * cached_sm_count(device);   // k_push_tile is built for 2 CTAs per SM
         g->use_tiles = true;
         if (const char* sv = getenv("MEDPY_GC_SOLVER")) if (!strcmp(sv, "v0")) g->use_tiles = false;
         if (const char* e1 = getenv("MEDPY_GC_ITERS")) if (atoi(e1) > 0) g->tile_iters = atoi(e1);
         if (const char* e2 = getenv("MEDPY_GC_PASSES0")) if (atoi(e2) > 0) g->passes0 = atoi(e2);
         if (const char* e3 = getenv("MEDPY_GC_PASSES_MAX")) if (atoi(e3) > 0) g->passes_max = atoi(e3);
+        if (const char* e4 = getenv("MEDPY_GC_COOP")) g->use_coop = atoi(e4) != 0;
+        {
+            int coop = 0, nb = 0;
+            const char* e5 = getenv("MEDPY_GC_BFS");
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+            if ((!e5 || strcmp(e5, "host") != 0) && coop &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_bfs_coop, TILE_VOX, 0) == cudaSuccess && nb >= 1)
+                g->coop_bfs_grid = nb * cached_sm_count(device);
+            else
+                cudaGetLastError();
+        }
+        {
+            int coop = 0, nb = 0;
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+            if (!g->use_coop) { /* not requested */ }
+            else if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_coop<double>, TILE_VOX, 0) != cudaSuccess || nb < 1) {
+                cudaGetLastError();
+                g->use_coop = false;
+            } else {
+                g->coop_grid = nb * cached_sm_count(device);
+            }
+        }
     }
     if (rc) { g_create_error = g->err; mgc_destroy(g); return rc; }
     if (cudaStreamCreate(&g->stream) != cudaSuccess) { g_create_error = "cudaStreamCreate failed"; mgc_destroy(g); return MGC_E_CUDA; }
@@ -586,7 +612,7 @@ int read_tcount(mgc_graph* g, int idx, int* out)
 // first call: solver state + first labels + first worklists in one pass (k_init_tile)
 int init_tiles(mgc_graph* g)
 {
-    CK(cudaMemsetAsync(g->d_tcount, 0, 64, g->stream));
+    CK(cudaMemsetAsync(g->d_tcount, 0, 256, g->stream));
     g->pl_sel[0] = g->pl_sel[1] = 0;
     k_init_tile<double><<<g->TL.ntiles, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S, g->rflag, rl(g, 0), g->pflag,
                                                                   pl(g, 0, 0), pl(g, 1, 0));
@@ -621,6 +647,23 @@ int relabel_tiles_begin(mgc_graph* g)
 int relabel_tiles_run(mgc_graph* g, int* any)
 {
     *any = 0;
+    if (g->coop_bfs_grid > 0) {
+        // all passes in one cooperative launch; the selector and the pass count come back through the control block
+        int hdr[4] = {0, g->pl_sel[0], g->pl_sel[1], g->rl_cur};
+        CK(cudaMemcpyAsync(g->d_tcount + CTL_CURSOR, hdr, sizeof(hdr), cudaMemcpyHostToDevice, g->stream));
+        int* it0 = g->rl_items[0]; int* it1 = g->rl_items[1];
+        void* args[] = {&g->L, &g->TL, &g->S.rmask, &g->S.height, &g->rflag, &it0, &it1, &g->d_tcount};
+        CK(cudaLaunchCooperativeKernel((void*)k_bfs_coop, dim3(g->coop_bfs_grid), dim3(TILE_VOX), args, 0, g->stream));
+        g->st.kernel_launches++;
+        int back[2] = {0, 0};   // [CTL_RLCUR], then [CTL_RELP] (not adjacent: two small copies)
+        CK(cudaMemcpyAsync(&back[0], g->d_tcount + CTL_RLCUR, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+        CK(cudaMemcpyAsync(&back[1], g->d_tcount + CTL_RELP, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+        CK(cudaStreamSynchronize(g->stream));
+        g->rl_cur = back[0];
+        g->st.relabel_sweeps += back[1];
+        *any = back[1] != 0;
+        return MGC_OK;
+    }
     for (;;) {
         const int cur = g->rl_cur;
         int pending = 0;
@@ -702,6 +745,38 @@ int count_active_tiles(mgc_graph* g, int64_t* out)
     return MGC_OK;
 }
 
+// One cooperative launch running the phases selected by `flags` (gc_persist.cuh); the host mirrors of the list
+// selectors and the statistics are refreshed from the control block afterwards.
+int solve_coop(mgc_graph* g, int flags, int passes, int64_t* active_out)
+{
+    int hdr[4] = {0, g->pl_sel[0], g->pl_sel[1], g->rl_cur};     // cursor, list selectors
+    CK(cudaMemcpyAsync(g->d_tcount + CTL_CURSOR, hdr, sizeof(hdr), cudaMemcpyHostToDevice, g->stream));
+    SolveLists SL;
+    SL.rl_items[0] = g->rl_items[0]; SL.rl_items[1] = g->rl_items[1];
+    for (int c = 0; c < 2; ++c) for (int b = 0; b < 2; ++b) SL.pl_items[c][b] = g->pl_items[c][b];
+    unsigned long long* active = g->d_count;
+    unsigned long long* timers = g->d_count + 1;
+    int iters = g->tile_iters, pmax = g->passes_max, mr = (int)(g->max_rounds > 0x7fffffff ? 0x7fffffff : g->max_rounds);
+    void* args[] = {&g->L, &g->TL, &g->S, &SL, &g->rflag, &g->pflag, &g->d_tcount, &active, &timers,
+                    &flags, &iters, &passes, &pmax, &mr};
+    CK(cudaLaunchCooperativeKernel((void*)k_solve_coop<double>, dim3(g->coop_grid), dim3(TILE_VOX), args, 0, g->stream));
+    g->st.kernel_launches++;
+    int ctl[20];
+    unsigned long long cnt[3];
+    CK(cudaMemcpyAsync(ctl, g->d_tcount, sizeof(ctl), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaMemcpyAsync(cnt, g->d_count, sizeof(cnt), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    g->pl_sel[0] = ctl[CTL_SEL0]; g->pl_sel[1] = ctl[CTL_SEL0 + 1]; g->rl_cur = ctl[CTL_RLCUR];
+    g->st.push_sweeps += ctl[CTL_PUSHP];
+    g->st.relabel_sweeps += ctl[CTL_RELP];
+    g->st.global_relabels += ctl[CTL_GREL];
+    g->st.ms_relabel += 1e-6 * (double)cnt[1];
+    g->st.ms_push += 1e-6 * (double)cnt[2];
+    if (flags & (SOLVE_F_COUNT | SOLVE_F_LOOP)) { g->st.active_last = (int64_t)cnt[0]; if (active_out) *active_out = (int64_t)cnt[0]; }
+    if (ctl[CTL_STATUS] != 0) FAIL(MGC_E_NOCONV, "push-relabel did not converge within the round cap");
+    return MGC_OK;
+}
+
 int solve_tiles(mgc_graph* g)
 {
     int rc = materialise_zeros(g);
@@ -709,6 +784,11 @@ int solve_tiles(mgc_graph* g)
     if (!g->state_init) {
         rc = init_tiles(g);
         if (rc) return rc;
+    }
+    if (g->use_coop) {
+        const int flags = SOLVE_F_LOOP | (g->labels_fresh ? 0 : SOLVE_F_RESET);
+        g->labels_fresh = false;
+        return solve_coop(g, flags, g->passes0, nullptr);
     }
     int passes = g->passes0;
     int64_t rounds = 0;
@@ -1178,7 +1258,7 @@ int mgc_slab_push(mgc_graph* g, int32_t n)
     if (!g || n < 0) return MGC_E_ARG;
     if (!g->state_init) FAIL(MGC_E_STATE, "call mgc_slab_begin first");
     CK(cudaSetDevice(g->device));
-    if (g->use_tiles) return push_tiles(g, n);
+    if (g->use_tiles) return g->use_coop ? solve_coop(g, SOLVE_F_PUSH, n, nullptr) : push_tiles(g, n);
     return push_sweeps(g, n, nullptr);
 }
 
@@ -1253,7 +1333,15 @@ int mgc_slab_relabel_relax(mgc_graph* g, int32_t* changed_out)
     if (!g || !changed_out) return MGC_E_ARG;
     CK(cudaSetDevice(g->device));
     int any = 0;
-    int rc = g->use_tiles ? relabel_tiles_run(g, &any) : relabel_relax(g, &any);
+    int rc = MGC_OK;
+    if (g->use_tiles && g->use_coop) {
+        const int64_t before = g->st.relabel_sweeps;
+        rc = solve_coop(g, SOLVE_F_BFS, 0, nullptr);
+        any = g->st.relabel_sweeps != before;
+        g->st.global_relabels--;      // counted by mgc_slab_relabel_begin already
+    } else {
+        rc = g->use_tiles ? relabel_tiles_run(g, &any) : relabel_relax(g, &any);
+    }
     if (rc) return rc;
     *changed_out = any ? 1 : 0;
     return MGC_OK;

@@ -90,7 +90,8 @@ __device__ __forceinline__ int tile_nbr(const Tiles& TL, int t, int k)
 __device__ __forceinline__ int load_heights(const Lattice& L, const TileCtx& c, const int* __restrict__ height, int* sh)
 {
     const int tid = threadIdx.x;
-    int h0 = c.inb ? height[c.v] : MGC_HINF;
+    // .cg loads: labels are read while other CTAs lower them (asynchronous BFS) -- never serve them from a stale L1 line
+    int h0 = c.inb ? __ldcg(height + c.v) : MGC_HINF;
     sh[hidx(c.lz + 1, c.ly + 1, c.lx + 1)] = h0;
     if (tid < 384) {
         const int face = tid >> 6, a = (tid >> 3) & 7, b = tid & 7;
@@ -106,7 +107,7 @@ __device__ __forceinline__ int load_heights(const Lattice& L, const TileCtx& c, 
         const int gz = c.tz * TILE + z, gy = c.ty * TILE + y, gx = c.tx * TILE + x;
         int h = MGC_HINF;
         if (gz >= 0 && gy >= 0 && gx >= 0 && gz < L.dim[0] && gy < L.dim[1] && gx < L.dim[2])
-            h = height[(unsigned)gz * L.stride[0] + (unsigned)gy * L.stride[1] + (unsigned)gx];
+            h = __ldcg(height + ((unsigned)gz * L.stride[0] + (unsigned)gy * L.stride[1] + (unsigned)gx));
         sh[hidx(z + 1, y + 1, x + 1)] = h;
     }
     return h0;
@@ -124,7 +125,7 @@ __device__ __forceinline__ int fetch_tile(const WorkList& cur, int* __restrict__
     __syncthreads();                       // previous tile fully done (also protects s_slot reuse)
     if (threadIdx.x == 0) {
         const int i = atomicAdd(cursor, 1);
-        *s_slot = (i < *cur.count) ? cur.items[i] : -1;
+        *s_slot = (i < *(volatile int*)cur.count) ? cur.items[i] : -1;
     }
     __syncthreads();
     return *s_slot;
@@ -181,8 +182,8 @@ __global__ void __launch_bounds__(TILE_VOX) k_init_tile(Lattice L, Tiles TL, Sta
 // later global relabels: labels from the (incrementally maintained) residual mask; 1 B read + 4 B written per voxel.
 // One thread per 8-voxel x-run of a tile row, consecutive threads on consecutive runs (coalesced); rflag must be
 // zero on entry (the host memsets it): a run that holds an unlabelled voxel with residual out-arcs lists its tile.
-__global__ void __launch_bounds__(256) k_relabel_reset(Lattice L, Tiles TL, const uint8_t* __restrict__ rmask,
-                                                       int* __restrict__ height, int* __restrict__ rflag, WorkList rl)
+__device__ __forceinline__ void relabel_reset_body(const Lattice& L, const Tiles& TL, const uint8_t* __restrict__ rmask,
+                                                   int* __restrict__ height, int* __restrict__ rflag, const WorkList& rl)
 {
     const unsigned ntx = (unsigned)TL.nt[2];
     const unsigned nruns = (unsigned)L.dim[0] * (unsigned)L.dim[1] * ntx;
@@ -218,9 +219,53 @@ __global__ void __launch_bounds__(256) k_relabel_reset(Lattice L, Tiles TL, cons
     }
 }
 
+__global__ void __launch_bounds__(256) k_relabel_reset(Lattice L, Tiles TL, const uint8_t* __restrict__ rmask,
+                                                       int* __restrict__ height, int* __restrict__ rflag, WorkList rl)
+{
+    relabel_reset_body(L, TL, rmask, height, rflag, rl);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // global relabel pass: persistent CTAs over the current worklist
 // ---------------------------------------------------------------------------------------------------
+// one tile visit of the global relabel: relax inside the tile until nothing changes, write back, list the face
+// neighbours whose halo changed.  `sh` = HALO_VOX ints of shared memory.
+__device__ __forceinline__ void relabel_visit(const Lattice& L, const Tiles& TL, const uint8_t* __restrict__ rmask,
+                                              int* __restrict__ height, int* __restrict__ rflag, const WorkList& next,
+                                              int t, int* sh)
+{
+    const TileCtx c = tile_ctx(L, TL, t);
+    if (threadIdx.x == 0) rflag[t] = 0;        // may be listed again by a neighbour from now on
+    const int h0 = load_heights(L, c, height, sh);
+    const unsigned m = c.own ? (rmask[c.v] & 0x3fu) : 0u;
+    __syncthreads();
+    const int me = hidx(c.lz + 1, c.ly + 1, c.lx + 1);
+    int h = h0;
+    for (;;) {
+        int changed = 0;
+        if (m && h > 1) {
+            int best = h;
+            if (m & 1u)  { const int hw = sh[me + hoff<0>()] + 1; best = hw < best ? hw : best; }
+            if (m & 2u)  { const int hw = sh[me + hoff<1>()] + 1; best = hw < best ? hw : best; }
+            if (m & 4u)  { const int hw = sh[me + hoff<2>()] + 1; best = hw < best ? hw : best; }
+            if (m & 8u)  { const int hw = sh[me + hoff<3>()] + 1; best = hw < best ? hw : best; }
+            if (m & 16u) { const int hw = sh[me + hoff<4>()] + 1; best = hw < best ? hw : best; }
+            if (m & 32u) { const int hw = sh[me + hoff<5>()] + 1; best = hw < best ? hw : best; }
+            if (best < h) { h = best; sh[me] = h; changed = 1; }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    if (h != h0) {
+        height[c.v] = h;
+        if (c.lz == 0 && c.tz > 0) list_push(rflag, next, tile_nbr(TL, t, 0));
+        if (c.lz == TILE - 1 && c.tz + 1 < TL.nt[0]) list_push(rflag, next, tile_nbr(TL, t, 1));
+        if (c.ly == 0 && c.ty > 0) list_push(rflag, next, tile_nbr(TL, t, 2));
+        if (c.ly == TILE - 1 && c.ty + 1 < TL.nt[1]) list_push(rflag, next, tile_nbr(TL, t, 3));
+        if (c.lx == 0 && c.tx > 0) list_push(rflag, next, tile_nbr(TL, t, 4));
+        if (c.lx == TILE - 1 && c.tx + 1 < TL.nt[2]) list_push(rflag, next, tile_nbr(TL, t, 5));
+    }
+}
+
 __global__ void __launch_bounds__(TILE_VOX) k_relabel_tile(Lattice L, Tiles TL, const uint8_t* __restrict__ rmask,
                                                            int* __restrict__ height, int* __restrict__ rflag,
                                                            WorkList cur, int* __restrict__ cursor, WorkList next)
@@ -230,36 +275,7 @@ __global__ void __launch_bounds__(TILE_VOX) k_relabel_tile(Lattice L, Tiles TL, 
     for (;;) {
         const int t = fetch_tile(cur, cursor, &s_slot);
         if (t < 0) break;
-        const TileCtx c = tile_ctx(L, TL, t);
-        if (threadIdx.x == 0) rflag[t] = 0;        // may be listed again by a neighbour from now on
-        const int h0 = load_heights(L, c, height, sh);
-        const unsigned m = c.own ? (rmask[c.v] & 0x3fu) : 0u;
-        __syncthreads();
-        const int me = hidx(c.lz + 1, c.ly + 1, c.lx + 1);
-        int h = h0;
-        for (;;) {
-            int changed = 0;
-            if (m && h > 1) {
-                int best = h;
-                if (m & 1u)  { const int hw = sh[me + hoff<0>()] + 1; best = hw < best ? hw : best; }
-                if (m & 2u)  { const int hw = sh[me + hoff<1>()] + 1; best = hw < best ? hw : best; }
-                if (m & 4u)  { const int hw = sh[me + hoff<2>()] + 1; best = hw < best ? hw : best; }
-                if (m & 8u)  { const int hw = sh[me + hoff<3>()] + 1; best = hw < best ? hw : best; }
-                if (m & 16u) { const int hw = sh[me + hoff<4>()] + 1; best = hw < best ? hw : best; }
-                if (m & 32u) { const int hw = sh[me + hoff<5>()] + 1; best = hw < best ? hw : best; }
-                if (best < h) { h = best; sh[me] = h; changed = 1; }
-            }
-            if (!__syncthreads_or(changed)) break;
-        }
-        if (h != h0) {
-            height[c.v] = h;
-            if (c.lz == 0 && c.tz > 0) list_push(rflag, next, tile_nbr(TL, t, 0));
-            if (c.lz == TILE - 1 && c.tz + 1 < TL.nt[0]) list_push(rflag, next, tile_nbr(TL, t, 1));
-            if (c.ly == 0 && c.ty > 0) list_push(rflag, next, tile_nbr(TL, t, 2));
-            if (c.ly == TILE - 1 && c.ty + 1 < TL.nt[1]) list_push(rflag, next, tile_nbr(TL, t, 3));
-            if (c.lx == 0 && c.tx > 0) list_push(rflag, next, tile_nbr(TL, t, 4));
-            if (c.lx == TILE - 1 && c.tx + 1 < TL.nt[2]) list_push(rflag, next, tile_nbr(TL, t, 5));
-        }
+        relabel_visit(L, TL, rmask, height, rflag, next, t, sh);
     }
 }
 
@@ -318,6 +334,81 @@ __device__ __forceinline__ void pull_dir(const TileCtx& c, const T* s_out, T& e,
     }
 }
 
+// one push/relabel discharge visit of tile t.  s_out = 6*TILE_VOX values, s_h = HALO_VOX ints of shared memory.
+template <typename T>
+__device__ __forceinline__ void push_visit(const Lattice& L, const Tiles& TL, const State<T>& S, int iters,
+                                           int* __restrict__ pflag, const WorkList& self_next, const WorkList& other_next,
+                                           int t, T* s_out, int* s_h)
+{
+    const TileCtx c = tile_ctx(L, TL, t);
+    const int tid = threadIdx.x;
+    const int me = hidx(c.lz + 1, c.ly + 1, c.lx + 1);
+    if (tid == 0) pflag[t] = 0;
+    const int h0 = load_heights(L, c, S.height, s_h);
+    T e = 0, scap = 0, sf = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
+    if (c.inb) {
+        e = S.excess[c.v];
+        c0 = S.cap[0][c.v]; c1 = S.cap[1][c.v]; c2 = S.cap[2][c.v];
+        c3 = S.cap[3][c.v]; c4 = S.cap[4][c.v]; c5 = S.cap[5][c.v];
+        const T tr = S.tr[c.v];
+        if (tr < 0) { scap = -tr; sf = S.sink[c.v]; }
+    }
+    int h = h0;
+    unsigned nbr_listed = 0, dirty = 0;     // dirty: bit k = cap k changed, 64 = excess, 128 = sink flow
+    __syncthreads();
+
+    for (int it = 0; it < iters; ++it) {
+        // ---- push phase: decisions from the label snapshot, own registers updated, outflow published ----
+        const int act = (c.own && e > 0 && h < MGC_HINF) ? 1 : 0;
+        int newh = h;
+        if (act) {
+            if (scap > 0) {                      // the sink sits at height 0: always admissible
+                const T rr = scap - sf;
+                if (rr > 0) {
+                    if (e < rr) { sf += e; e = 0; } else { e -= rr; sf = scap; }   // saturation is exact
+                    dirty |= 64u | 128u;
+                }
+            }
+            int minh = MGC_HINF;
+            push_dir<0>(L, TL, S, c, s_h, s_out, me, h, e, c0, minh, pflag, other_next, nbr_listed, dirty);
+            push_dir<1>(L, TL, S, c, s_h, s_out, me, h, e, c1, minh, pflag, other_next, nbr_listed, dirty);
+            push_dir<2>(L, TL, S, c, s_h, s_out, me, h, e, c2, minh, pflag, other_next, nbr_listed, dirty);
+            push_dir<3>(L, TL, S, c, s_h, s_out, me, h, e, c3, minh, pflag, other_next, nbr_listed, dirty);
+            push_dir<4>(L, TL, S, c, s_h, s_out, me, h, e, c4, minh, pflag, other_next, nbr_listed, dirty);
+            push_dir<5>(L, TL, S, c, s_h, s_out, me, h, e, c5, minh, pflag, other_next, nbr_listed, dirty);
+            // excess left => no admissible arc left => relabel above the lowest residual neighbour
+            if (e > 0) newh = (minh >= MGC_HINF) ? MGC_HINF : minh + 1;
+        } else {
+            s_out[0 * TILE_VOX + tid] = 0; s_out[1 * TILE_VOX + tid] = 0; s_out[2 * TILE_VOX + tid] = 0;
+            s_out[3 * TILE_VOX + tid] = 0; s_out[4 * TILE_VOX + tid] = 0; s_out[5 * TILE_VOX + tid] = 0;
+        }
+        if (!__syncthreads_or(act)) break;       // nothing moved in this tile: done
+        // ---- pull phase: every voxel collects what its in-tile neighbours sent; labels are published ----
+        pull_dir<0>(c, s_out, e, c0, dirty); pull_dir<1>(c, s_out, e, c1, dirty); pull_dir<2>(c, s_out, e, c2, dirty);
+        pull_dir<3>(c, s_out, e, c3, dirty); pull_dir<4>(c, s_out, e, c4, dirty); pull_dir<5>(c, s_out, e, c5, dirty);
+        if (newh != h) { h = newh; s_h[me] = h; }
+        __syncthreads();
+    }
+
+    // ---- write back what changed (this CTA is the only writer of its own voxels during this launch) ----
+    if (c.inb && (dirty || h != h0)) {
+        if (dirty & 64u) S.excess[c.v] = e;
+        if (dirty & 1u) S.cap[0][c.v] = c0;
+        if (dirty & 2u) S.cap[1][c.v] = c1;
+        if (dirty & 4u) S.cap[2][c.v] = c2;
+        if (dirty & 8u) S.cap[3][c.v] = c3;
+        if (dirty & 16u) S.cap[4][c.v] = c4;
+        if (dirty & 32u) S.cap[5][c.v] = c5;
+        if (h != h0) S.height[c.v] = h;
+        if (dirty & 128u) S.sink[c.v] = sf;
+        unsigned m = (c0 > 0 ? 1u : 0u) | (c1 > 0 ? 2u : 0u) | (c2 > 0 ? 4u : 0u) | (c3 > 0 ? 8u : 0u) |
+                     (c4 > 0 ? 16u : 0u) | (c5 > 0 ? 32u : 0u) | ((scap - sf > 0) ? RM_SINK : 0u);
+        S.rmask[c.v] = (uint8_t)m;
+    }
+    const int still = (c.own && e > 0 && h < MGC_HINF) ? 1 : 0;
+    if (__syncthreads_or(still) && tid == 0) list_push(pflag, self_next, t);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(TILE_VOX, 2) k_push_tile(Lattice L, Tiles TL, State<T> S, int iters,
                                                            int* __restrict__ pflag, WorkList cur, int* __restrict__ cursor,
@@ -329,87 +420,29 @@ __global__ void __launch_bounds__(TILE_VOX, 2) k_push_tile(Lattice L, Tiles TL, 
     for (;;) {
         const int t = fetch_tile(cur, cursor, &s_slot);
         if (t < 0) break;
-        const TileCtx c = tile_ctx(L, TL, t);
-        const int tid = threadIdx.x;
-        const int me = hidx(c.lz + 1, c.ly + 1, c.lx + 1);
-        if (tid == 0) pflag[t] = 0;
-        const int h0 = load_heights(L, c, S.height, s_h);
-        T e = 0, scap = 0, sf = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
-        if (c.inb) {
-            e = S.excess[c.v];
-            c0 = S.cap[0][c.v]; c1 = S.cap[1][c.v]; c2 = S.cap[2][c.v];
-            c3 = S.cap[3][c.v]; c4 = S.cap[4][c.v]; c5 = S.cap[5][c.v];
-            const T tr = S.tr[c.v];
-            if (tr < 0) { scap = -tr; sf = S.sink[c.v]; }
-        }
-        int h = h0;
-        unsigned nbr_listed = 0, dirty = 0;     // dirty: bit k = cap k changed, 64 = excess, 128 = sink flow
-        __syncthreads();
-
-        for (int it = 0; it < iters; ++it) {
-            // ---- push phase: decisions from the label snapshot, own registers updated, outflow published ----
-            const int act = (c.own && e > 0 && h < MGC_HINF) ? 1 : 0;
-            int newh = h;
-            if (act) {
-                if (scap > 0) {                      // the sink sits at height 0: always admissible
-                    const T rr = scap - sf;
-                    if (rr > 0) {
-                        if (e < rr) { sf += e; e = 0; } else { e -= rr; sf = scap; }   // saturation is exact
-                        dirty |= 64u | 128u;
-                    }
-                }
-                int minh = MGC_HINF;
-                push_dir<0>(L, TL, S, c, s_h, s_out, me, h, e, c0, minh, pflag, other_next, nbr_listed, dirty);
-                push_dir<1>(L, TL, S, c, s_h, s_out, me, h, e, c1, minh, pflag, other_next, nbr_listed, dirty);
-                push_dir<2>(L, TL, S, c, s_h, s_out, me, h, e, c2, minh, pflag, other_next, nbr_listed, dirty);
-                push_dir<3>(L, TL, S, c, s_h, s_out, me, h, e, c3, minh, pflag, other_next, nbr_listed, dirty);
-                push_dir<4>(L, TL, S, c, s_h, s_out, me, h, e, c4, minh, pflag, other_next, nbr_listed, dirty);
-                push_dir<5>(L, TL, S, c, s_h, s_out, me, h, e, c5, minh, pflag, other_next, nbr_listed, dirty);
-                // excess left => no admissible arc left => relabel above the lowest residual neighbour
-                if (e > 0) newh = (minh >= MGC_HINF) ? MGC_HINF : minh + 1;
-            } else {
-                s_out[0 * TILE_VOX + tid] = 0; s_out[1 * TILE_VOX + tid] = 0; s_out[2 * TILE_VOX + tid] = 0;
-                s_out[3 * TILE_VOX + tid] = 0; s_out[4 * TILE_VOX + tid] = 0; s_out[5 * TILE_VOX + tid] = 0;
-            }
-            if (!__syncthreads_or(act)) break;       // nothing moved in this tile: done
-            // ---- pull phase: every voxel collects what its in-tile neighbours sent; labels are published ----
-            pull_dir<0>(c, s_out, e, c0, dirty); pull_dir<1>(c, s_out, e, c1, dirty); pull_dir<2>(c, s_out, e, c2, dirty);
-            pull_dir<3>(c, s_out, e, c3, dirty); pull_dir<4>(c, s_out, e, c4, dirty); pull_dir<5>(c, s_out, e, c5, dirty);
-            if (newh != h) { h = newh; s_h[me] = h; }
-            __syncthreads();
-        }
-
-        // ---- write back what changed (this CTA is the only writer of its own voxels during this launch) ----
-        if (c.inb && (dirty || h != h0)) {
-            if (dirty & 64u) S.excess[c.v] = e;
-            if (dirty & 1u) S.cap[0][c.v] = c0;
-            if (dirty & 2u) S.cap[1][c.v] = c1;
-            if (dirty & 4u) S.cap[2][c.v] = c2;
-            if (dirty & 8u) S.cap[3][c.v] = c3;
-            if (dirty & 16u) S.cap[4][c.v] = c4;
-            if (dirty & 32u) S.cap[5][c.v] = c5;
-            if (h != h0) S.height[c.v] = h;
-            if (dirty & 128u) S.sink[c.v] = sf;
-            unsigned m = (c0 > 0 ? 1u : 0u) | (c1 > 0 ? 2u : 0u) | (c2 > 0 ? 4u : 0u) | (c3 > 0 ? 8u : 0u) |
-                         (c4 > 0 ? 16u : 0u) | (c5 > 0 ? 32u : 0u) | ((scap - sf > 0) ? RM_SINK : 0u);
-            S.rmask[c.v] = (uint8_t)m;
-        }
-        const int still = (c.own && e > 0 && h < MGC_HINF) ? 1 : 0;
-        if (__syncthreads_or(still) && tid == 0) list_push(pflag, self_next, t);
+        push_visit<T>(L, TL, S, iters, pflag, self_next, other_next, t, s_out, s_h);
     }
 }
 
 // exact count of active voxels, scanning only the tiles of a worklist (a superset of the tiles that can hold one)
 template <typename T>
-__global__ void __launch_bounds__(TILE_VOX) k_count_active_tiles(Lattice L, Tiles TL, State<T> S, WorkList wl,
-                                                                 unsigned long long* __restrict__ count)
+__device__ __forceinline__ void count_active_body(const Lattice& L, const Tiles& TL, const State<T>& S, const WorkList& wl,
+                                                  unsigned long long* __restrict__ count)
 {
-    for (int i = blockIdx.x; i < *wl.count; i += gridDim.x) {
+    const int n = *(volatile int*)wl.count;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const TileCtx c = tile_ctx(L, TL, wl.items[i]);
         const bool act = c.own && (S.excess[c.v] > 0) && (S.height[c.v] < MGC_HINF);
         const unsigned b = __ballot_sync(0xffffffffu, act);
         if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, (unsigned long long)__popc(b));
     }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TILE_VOX) k_count_active_tiles(Lattice L, Tiles TL, State<T> S, WorkList wl,
+                                                                 unsigned long long* __restrict__ count)
+{
+    count_active_body<T>(L, TL, S, wl, count);
 }
 
 // ---------------------------------------------------------------------------------------------------

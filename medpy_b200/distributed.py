@@ -219,7 +219,37 @@ def graphcut_slab(fg_markers, bg_markers, image=None, boundary=None, sigma=None,
 # ------------------------------------------------------------------------------------------------------
 # bench support (bench.py --gpus N, launched with torchrun)
 # ------------------------------------------------------------------------------------------------------
-def bench_slab(vol, args, rank, world, local_rank):
+def slab_volume(shape, rank, world, seed=0):
+    """This rank's planes (+ ghost planes) of the synthetic two-blob workload and the GLOBAL sigma: every rank
+    generates only what it needs (the generator seeds each plane separately) and the per-plane partial sums of the
+    RMS neighbour difference are all-gathered and added with fsum, so sigma is bit-identical to the single-process
+    value whatever the partition."""
+    import torch
+    import torch.distributed as dist
+    from . import synthetic
+    z0, z1 = slab_bounds(shape[0], world, rank)
+    a = z0 - (1 if z0 > 0 else 0)
+    b = z1 + (1 if z1 < shape[0] else 0)
+    vol = synthetic.two_blob_volume(shape, seed=seed, planes=(a, b))
+    own = vol["image"][z0 - a: z0 - a + (z1 - z0)]
+    nxt = vol["image"][z1 - a] if z1 < shape[0] else None
+    parts = synthetic.neighbour_difference_partials(own, next_plane=nxt)
+    pmax = max(slab_bounds(shape[0], world, r)[1] - slab_bounds(shape[0], world, r)[0] for r in range(world))
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    buf = torch.zeros(pmax, dtype=torch.float64, device=dev)
+    buf[: parts.size] = torch.from_numpy(parts).to(dev)
+    allp = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(allp, buf)
+    vals = []
+    for r, t in enumerate(allp):
+        c0, c1 = slab_bounds(shape[0], world, r)
+        vals.extend(t[: c1 - c0].cpu().tolist())
+    vol["sigma"] = float(math.sqrt(math.fsum(vals) / synthetic.neighbour_pair_count(shape)))
+    vol["shape"] = tuple(shape)
+    return vol
+
+
+def bench_slab(shape, args, rank, world, local_rank):
     """Strong-scaling run of bench.py's workload: the volume is partitioned once, the slab inputs stay resident
     in HBM, each timed step rebuilds the terms, solves and extracts the mask.  Returns the dict bench.py prints
     (meaningful on rank 0)."""
@@ -228,13 +258,14 @@ def bench_slab(vol, args, rank, world, local_rank):
     import torch.distributed as dist
     from bench import ClockSampler, measured_peak, UNIT  # noqa
     dev = torch.device("cuda", local_rank)
-    shape = vol["shape"]
     n = int(numpy.prod(shape))
+    vol = slab_volume(shape, rank, world)
     s = SlabSolver(shape, rank=rank, world=world, device=local_rank)
-    d_img = torch.from_numpy(numpy.ascontiguousarray(s.local_slice(vol["image"]))).to(dev)
-    d_prob = torch.from_numpy(numpy.ascontiguousarray(s.local_slice(vol["prob"]))).to(dev)
-    d_fg = torch.from_numpy(numpy.ascontiguousarray(s.local_slice(vol["fg"])).view(numpy.uint8)).to(dev)
-    d_bg = torch.from_numpy(numpy.ascontiguousarray(s.local_slice(vol["bg"])).view(numpy.uint8)).to(dev)
+    s.local_slice = lambda arr: arr          # the arrays already are this rank's planes
+    d_img = torch.from_numpy(numpy.ascontiguousarray(vol["image"])).to(dev)
+    d_prob = torch.from_numpy(numpy.ascontiguousarray(vol["prob"])).to(dev)
+    d_fg = torch.from_numpy(numpy.ascontiguousarray(vol["fg"]).view(numpy.uint8)).to(dev)
+    d_bg = torch.from_numpy(numpy.ascontiguousarray(vol["bg"]).view(numpy.uint8)).to(dev)
     d_mask = torch.empty((s.z1 - s.z0,) + tuple(shape[1:]), dtype=torch.uint8, device=dev)
     launches = []
 
@@ -319,4 +350,4 @@ def bench_slab(vol, args, rank, world, local_rank):
     return {"value": n * args.steps / (ms * 1e-3) / 1e6, "ms_per_step": ms / args.steps, "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(nl.item()), "roofline": roof, "energy": energy, "fg_voxels": int(fgv.item()),
             "push_sweeps": s.stats["push_passes"], "global_relabels": s.stats["global_relabels"],
-            "relabel_sweeps": s.stats["relabel_rounds"]}
+            "relabel_sweeps": s.stats["relabel_rounds"], "sigma": vol["sigma"]}
