@@ -1,0 +1,34 @@
+"""Minimal stand-ins for the two names the voxel CLI takes from ``medpy.core``
+(reference: medpy/core/logger.py:35-148, medpy/core/exceptions.py:31)."""
+import logging
+import sys
+
+
+class ArgumentError(Exception):
+    """Raised for invalid command line arguments."""
+
+
+class ImageLoadingError(Exception):
+    """Raised when an image cannot be read."""
+
+
+class ImageSavingError(Exception):
+    """Raised when an image cannot be written."""
+
+
+class Logger(logging.Logger):
+    """Process-wide logger writing to stdout, WARNING by default; ``Logger.getInstance()`` returns the singleton."""
+
+    _instance = None
+
+    def __init__(self, name="MedPyLogger", level=logging.WARNING):
+        super().__init__(name, level)
+        handler = logging.StreamHandler(sys.stdout)
+        handler.setFormatter(logging.Formatter("%(asctime)s %(levelname)s: %(message)s"))
+        self.addHandler(handler)
+
+    @classmethod
+    def getInstance(cls):
+        if cls._instance is None:
+            cls._instance = cls()
+        return cls._instance

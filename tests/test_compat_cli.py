@@ -1,0 +1,89 @@
+"""The reference CLI against the import shim (CPU part) and our own CLI on the GPU."""
+import os
+import subprocess
+import sys
+
+import numpy
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+COMPAT = os.path.join(ROOT, "medpy_b200", "compat")
+REF_CLI = "/root/reference/bin/medpy_graphcut_voxel.py"
+
+
+def _write_case(tmp_path, shape=(12, 10, 9)):
+    sys.path.insert(0, COMPAT)
+    try:
+        from medpy.io import save, Header
+    finally:
+        sys.path.remove(COMPAT)
+    from medpy_b200 import synthetic
+    vol = synthetic.two_blob_volume(shape, seed=2, with_prob=False)
+    # MedPy's convention: arrays are x,y,z -> transpose our z,y,x volume
+    img_xyz = numpy.ascontiguousarray(vol["image"]).T
+    markers = (vol["fg"].astype(numpy.uint8) + 2 * vol["bg"].astype(numpy.uint8)).T
+    hdr = Header(spacing=(1.0, 1.0, 2.0), offset=(0.0, 0.0, 0.0))
+    ip, mp = str(tmp_path / "img.mha"), str(tmp_path / "markers.mha")
+    save(img_xyz, ip, hdr, True)
+    save(markers, mp, hdr, True)
+    return vol, ip, mp
+
+
+def test_metaimage_roundtrip_and_xyz_order(tmp_path):
+    sys.path.insert(0, COMPAT)
+    try:
+        import importlib
+        import medpy.io as mio
+        importlib.reload(mio)
+        a = numpy.arange(2 * 3 * 4, dtype=numpy.float32).reshape(2, 3, 4)  # x, y, z
+        p = str(tmp_path / "a.mha")
+        mio.save(a, p, mio.Header(spacing=(1, 2, 3), offset=(0, 0, 0)), True)
+        b, hdr = mio.load(p)
+        assert b.shape == (2, 3, 4) and numpy.array_equal(a, b)
+        assert not b.flags.c_contiguous and b.flags.f_contiguous      # transposed view, like the reference's load()
+        assert mio.header.get_voxel_spacing(hdr) == (1.0, 2.0, 3.0)
+        with pytest.warns(DeprecationWarning):
+            assert mio.header.get_pixel_spacing(hdr) == (1.0, 2.0, 3.0)
+    finally:
+        sys.path.remove(COMPAT)
+        for k in [k for k in sys.modules if k == "medpy" or k.startswith("medpy.")]:
+            del sys.modules[k]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CLI), reason="reference tree not present")
+def test_reference_cli_runs_unchanged_up_to_the_device(tmp_path):
+    """bin/medpy_graphcut_voxel.py, executed in place and unmodified, imports medpy.* from the shim, parses its
+    arguments, loads the images, splits the markers and reaches graph_from_voxels; without a GPU that is where the
+    product refuses (no CPU fallback); with one it must finish and write the mask."""
+    import torch
+    vol, ip, mp = _write_case(tmp_path)
+    out = str(tmp_path / "out.mha")
+    env = dict(os.environ, PYTHONPATH=COMPAT + os.pathsep + ROOT, PYTHONDONTWRITEBYTECODE="1")
+    r = subprocess.run([sys.executable, REF_CLI, "15.0", ip, mp, out, "--boundary", "diff_exp", "-f"],
+                       env=env, capture_output=True, text=True, timeout=300)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert os.path.exists(out)
+    else:
+        assert r.returncode != 0
+        assert "no CPU path" in r.stderr or "CUDA" in r.stderr, r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_own_cli_matches_oracle(tmp_path):
+    from oracle import energy_terms as et, solvers
+    vol, ip, mp = _write_case(tmp_path, shape=(20, 16, 18))
+    out = str(tmp_path / "out.mha")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "medpy_b200", "cli", "graphcut_voxel.py"), "15.0", ip, mp, out,
+                        "--boundary", "diff_exp", "-s", "-f"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    sys.path.insert(0, COMPAT)
+    try:
+        from medpy.io import load
+        mask_xyz, _ = load(out)
+    finally:
+        sys.path.remove(COMPAT)
+    # spacing (1,1,2) is in x,y,z order = the CLI's array order; our volume is z,y,x -> reversed
+    prob = et.build_problem(vol["fg"], vol["bg"], boundary=("difference_exponential", vol["image"], 15.0, (2.0, 1.0, 1.0)))
+    oflow, omask, _ = solvers.solve_port(prob)
+    assert numpy.array_equal(mask_xyz.T.astype(numpy.uint8), omask)
