@@ -181,16 +181,19 @@ int mgc_slab_push(mgc_graph* g, int32_t n);
  * Pass NULL for a side without neighbour. */
 int mgc_slab_pack(mgc_graph* g, int32_t* h_lo, double* f_lo, int32_t* h_hi, double* f_hi);
 /* Apply the neighbours' messages: ghost-plane heights, and received flow added to excess and to the reverse
- * residual of my border plane.  *ghost_changed_out = 1 if any ghost label differs from before. */
+ * residual of my border plane.  `changed_dev` (DEVICE pointer or NULL) is set to 1 by the kernel if any ghost label
+ * differs from before; the caller zeroes it and typically all-reduces it over the ranks.  No host synchronisation. */
 int mgc_slab_unpack(mgc_graph* g, const int32_t* h_lo, const double* f_lo, const int32_t* h_hi, const double* f_hi,
-                    int32_t* ghost_changed_out);
+                    int32_t* changed_dev);
 /* Global relabel, distributed: (re)start a backward BFS from the sink ... */
 int mgc_slab_relabel_begin(mgc_graph* g);
-/* ... relax locally until nothing changes (given the current ghost labels); *changed_out = 1 if any label
- * changed in this call. */
+/* ... relax locally until nothing changes (given the current ghost labels).  changed_out may be NULL (then the call
+ * does not synchronise with the host); otherwise *changed_out = 1 if any tile was visited in this call. */
 int mgc_slab_relabel_relax(mgc_graph* g, int32_t* changed_out);
 /* Voxels with excess > 0 and a finite label (owned planes only). */
 int mgc_slab_count_active(mgc_graph* g, int64_t* active_out);
+/* Same, written to a DEVICE counter (uint64) without synchronising with the host. */
+int mgc_slab_count_active_dev(mgc_graph* g, unsigned long long* count_dev);
 /* Finish: build the mask of the owned planes and this slab's share of the energy
  * (flow absorbed by the owned sink links + owned add_tweights constants). */
 int mgc_slab_finish(mgc_graph* g, double* energy_part);

@@ -628,7 +628,12 @@ int init_tiles(mgc_graph* g)
 // begin: labels from the residual mask + a fresh worklist (skipped when k_init_tile just produced both)
 int relabel_tiles_begin(mgc_graph* g)
 {
-    if (g->labels_fresh) { g->labels_fresh = false; g->rl_cur = 0; return MGC_OK; }
+    if (g->labels_fresh) {
+        g->labels_fresh = false;
+        g->rl_cur = 0;
+        CK(cudaMemsetAsync(g->d_tcount + CTL_RLCUR, 0, sizeof(int), g->stream));
+        return MGC_OK;
+    }
     CK(cudaMemsetAsync(g->d_tcount, 0, 2 * sizeof(int), g->stream));
     CK(cudaMemsetAsync(g->rflag, 0, (size_t)g->TL.ntiles * sizeof(int), g->stream));
     {
@@ -639,29 +644,30 @@ int relabel_tiles_begin(mgc_graph* g)
     }
     g->st.kernel_launches++;
     g->rl_cur = 0;
+    CK(cudaMemsetAsync(g->d_tcount + CTL_RLCUR, 0, sizeof(int), g->stream));
     CK(cudaGetLastError());
     return MGC_OK;
 }
 
 // run passes until the current worklist is empty; *any = 1 if any tile was visited
-int relabel_tiles_run(mgc_graph* g, int* any)
+int relabel_tiles_run(mgc_graph* g, int* any, bool want_any = true)
 {
     *any = 0;
     if (g->coop_bfs_grid > 0) {
-        // all passes in one cooperative launch; the selector and the pass count come back through the control block
-        int hdr[4] = {0, g->pl_sel[0], g->pl_sel[1], g->rl_cur};
-        CK(cudaMemcpyAsync(g->d_tcount + CTL_CURSOR, hdr, sizeof(hdr), cudaMemcpyHostToDevice, g->stream));
+        // all passes in one cooperative launch; the list selector lives in the control block (device side), so the
+        // host does not have to synchronise unless the caller wants to know whether anything moved
+        CK(cudaMemsetAsync(g->d_tcount + CTL_CURSOR, 0, sizeof(int), g->stream));
         int* it0 = g->rl_items[0]; int* it1 = g->rl_items[1];
         void* args[] = {&g->L, &g->TL, &g->S.rmask, &g->S.height, &g->rflag, &it0, &it1, &g->d_tcount};
         CK(cudaLaunchCooperativeKernel((void*)k_bfs_coop, dim3(g->coop_bfs_grid), dim3(TILE_VOX), args, 0, g->stream));
         g->st.kernel_launches++;
-        int back[2] = {0, 0};   // [CTL_RLCUR], then [CTL_RELP] (not adjacent: two small copies)
-        CK(cudaMemcpyAsync(&back[0], g->d_tcount + CTL_RLCUR, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
-        CK(cudaMemcpyAsync(&back[1], g->d_tcount + CTL_RELP, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
-        CK(cudaStreamSynchronize(g->stream));
-        g->rl_cur = back[0];
-        g->st.relabel_sweeps += back[1];
-        *any = back[1] != 0;
+        g->st.relabel_sweeps++;     // passes are counted on the device (ctl[CTL_RELP]); one launch here
+        if (want_any) {
+            int relp = 0;
+            CK(cudaMemcpyAsync(&relp, g->d_tcount + CTL_RELP, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+            CK(cudaStreamSynchronize(g->stream));
+            *any = relp != 0;
+        }
         return MGC_OK;
     }
     for (;;) {
@@ -724,6 +730,7 @@ int push_tiles(mgc_graph* g, int passes)
     }
     g->st.push_sweeps += passes;
     CK(cudaGetLastError());
+    if (g->slab) return MGC_OK;      // slabs are stepped asynchronously: no per-call timing synchronisation
     cudaEventRecord(g->ev[3], g->stream);
     CK(cudaEventSynchronize(g->ev[3]));
     { float ms = 0; cudaEventElapsedTime(&ms, g->ev[2], g->ev[3]); g->st.ms_push += ms; }
@@ -1283,13 +1290,12 @@ int mgc_slab_pack(mgc_graph* g, int32_t* h_lo, double* f_lo, int32_t* h_hi, doub
 }
 
 int mgc_slab_unpack(mgc_graph* g, const int32_t* h_lo, const double* f_lo, const int32_t* h_hi, const double* f_hi,
-                    int32_t* ghost_changed_out)
+                    int32_t* changed_dev)
 {
     if (!g) return MGC_E_ARG;
     CK(cudaSetDevice(g->device));
     const unsigned P = g->L.plane;
     const unsigned nb = (P + 255u) / 256u;
-    CK(cudaMemsetAsync(g->d_flags + 1, 0, sizeof(int), g->stream));
     for (int side = 0; side < 2; ++side) {
         const bool have = side == 0 ? (g->ghost_lo && h_lo && f_lo) : (g->ghost_hi && h_hi && f_hi);
         if (!have) continue;
@@ -1299,22 +1305,17 @@ int mgc_slab_unpack(mgc_graph* g, const int32_t* h_lo, const double* f_lo, const
         const int32_t* hin = side == 0 ? h_lo : h_hi;
         const double* fin = side == 0 ? f_lo : f_hi;
         if (g->use_tiles) {
-            k_slab_unpack_tiles<double><<<nb, 256, 0, g->stream>>>(g->L, g->TL, g->S, zg, zb, k, hin, fin, g->rflag, rl(g, g->rl_cur),
-                                                                  g->pflag, pl(g, 0, g->pl_sel[0]), pl(g, 1, g->pl_sel[1]), g->d_flags + 1);
+            k_slab_unpack_tiles<double><<<nb, 256, 0, g->stream>>>(g->L, g->TL, g->S, zg, zb, k, hin, fin, g->rflag, rl(g, 0), rl(g, 1),
+                                                                  g->coop_bfs_grid > 0 ? g->d_tcount + CTL_RLCUR : nullptr, g->rl_cur,
+                                                                  g->pflag, pl(g, 0, g->pl_sel[0]), pl(g, 1, g->pl_sel[1]), changed_dev);
         } else {
             const size_t border = (size_t)zb * P, ghost = (size_t)zg * P;
             k_slab_unpack<double><<<nb, 256, 0, g->stream>>>(P, g->S.height + ghost, g->S.excess + border, g->S.cap[k] + border,
-                                                            hin, fin, g->d_flags + 1);
+                                                            hin, fin, changed_dev);
         }
         g->st.kernel_launches++;
     }
     CK(cudaGetLastError());
-    if (ghost_changed_out) {
-        int ch = 0;
-        CK(cudaMemcpyAsync(&ch, g->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
-        CK(cudaStreamSynchronize(g->stream));
-        *ghost_changed_out = ch;
-    }
     return MGC_OK;
 }
 
@@ -1330,7 +1331,7 @@ int mgc_slab_relabel_begin(mgc_graph* g)
 
 int mgc_slab_relabel_relax(mgc_graph* g, int32_t* changed_out)
 {
-    if (!g || !changed_out) return MGC_E_ARG;
+    if (!g) return MGC_E_ARG;
     CK(cudaSetDevice(g->device));
     int any = 0;
     int rc = MGC_OK;
@@ -1340,10 +1341,10 @@ int mgc_slab_relabel_relax(mgc_graph* g, int32_t* changed_out)
         any = g->st.relabel_sweeps != before;
         g->st.global_relabels--;      // counted by mgc_slab_relabel_begin already
     } else {
-        rc = g->use_tiles ? relabel_tiles_run(g, &any) : relabel_relax(g, &any);
+        rc = g->use_tiles ? relabel_tiles_run(g, &any, changed_out != nullptr) : relabel_relax(g, &any);
     }
     if (rc) return rc;
-    *changed_out = any ? 1 : 0;
+    if (changed_out) *changed_out = any ? 1 : 0;
     return MGC_OK;
 }
 
@@ -1352,6 +1353,23 @@ int mgc_slab_count_active(mgc_graph* g, int64_t* active_out)
     if (!g || !active_out) return MGC_E_ARG;
     CK(cudaSetDevice(g->device));
     return g->use_tiles ? count_active_tiles(g, active_out) : count_active(g, active_out);
+}
+
+int mgc_slab_count_active_dev(mgc_graph* g, unsigned long long* count_dev)
+{
+    if (!g || !count_dev) return MGC_E_ARG;
+    CK(cudaSetDevice(g->device));
+    CK(cudaMemsetAsync(count_dev, 0, sizeof(unsigned long long), g->stream));
+    if (g->use_tiles) {
+        for (int color = 0; color < 2; ++color)
+            k_count_active_tiles<double><<<g->n_ctas * 2, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S, pl(g, color, g->pl_sel[color]), count_dev);
+        g->st.kernel_launches += 2;
+    } else {
+        k_count_active<double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, count_dev);
+        g->st.kernel_launches++;
+    }
+    CK(cudaGetLastError());
+    return MGC_OK;
 }
 
 int mgc_slab_finish(mgc_graph* g, double* energy_part)

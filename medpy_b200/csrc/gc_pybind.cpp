@@ -215,16 +215,27 @@ public:
         { py::gil_scoped_release rel; rc = mgc_slab_pack(g_, (int32_t*)hlo, (double*)flo, (int32_t*)hhi, (double*)fhi); }
         check(rc, g_);
     }
-    int slab_unpack(uintptr_t hlo, uintptr_t flo, uintptr_t hhi, uintptr_t fhi)
+    void slab_unpack(uintptr_t hlo, uintptr_t flo, uintptr_t hhi, uintptr_t fhi, uintptr_t changed_dev)
     {
         int rc;
-        int32_t changed = 0;
-        { py::gil_scoped_release rel; rc = mgc_slab_unpack(g_, (const int32_t*)hlo, (const double*)flo, (const int32_t*)hhi, (const double*)fhi, &changed); }
+        { py::gil_scoped_release rel; rc = mgc_slab_unpack(g_, (const int32_t*)hlo, (const double*)flo, (const int32_t*)hhi, (const double*)fhi, (int32_t*)changed_dev); }
         check(rc, g_);
-        return changed;
+    }
+    void slab_count_active_dev(uintptr_t count_dev)
+    {
+        int rc;
+        { py::gil_scoped_release rel; rc = mgc_slab_count_active_dev(g_, (unsigned long long*)count_dev); }
+        check(rc, g_);
     }
     void slab_relabel_begin() { int rc; { py::gil_scoped_release rel; rc = mgc_slab_relabel_begin(g_); } check(rc, g_); }
-    int slab_relabel_relax() { int32_t c = 0; int rc; { py::gil_scoped_release rel; rc = mgc_slab_relabel_relax(g_, &c); } check(rc, g_); return c; }
+    int slab_relabel_relax(bool want_changed)
+    {
+        int32_t c = 0;
+        int rc;
+        { py::gil_scoped_release rel; rc = mgc_slab_relabel_relax(g_, want_changed ? &c : nullptr); }
+        check(rc, g_);
+        return c;
+    }
     int64_t slab_count_active() { int64_t a = 0; int rc; { py::gil_scoped_release rel; rc = mgc_slab_count_active(g_, &a); } check(rc, g_); return a; }
     double slab_finish() { double e = 0; int rc; { py::gil_scoped_release rel; rc = mgc_slab_finish(g_, &e); } check(rc, g_); return e; }
 
@@ -270,7 +281,8 @@ PYBIND11_MODULE(_mgc, m)
         .def("slab_pack", &PyGraph::slab_pack)
         .def("slab_unpack", &PyGraph::slab_unpack)
         .def("slab_relabel_begin", &PyGraph::slab_relabel_begin)
-        .def("slab_relabel_relax", &PyGraph::slab_relabel_relax)
+        .def("slab_relabel_relax", &PyGraph::slab_relabel_relax, py::arg("want_changed") = false)
+        .def("slab_count_active_dev", &PyGraph::slab_count_active_dev)
         .def("slab_count_active", &PyGraph::slab_count_active)
         .def("slab_finish", &PyGraph::slab_finish)
         .def_property_readonly("shape", &PyGraph::shape);

@@ -202,7 +202,7 @@ __global__ void k_slab_unpack(unsigned plane, int* __restrict__ height_ghost, T*
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= plane) return;
     int hn = h_in[i];
-    if (height_ghost[i] != hn) { height_ghost[i] = hn; *changed = 1; }
+    if (height_ghost[i] != hn) { height_ghost[i] = hn; if (changed) *changed = 1; }
     double f = f_in[i];
     if (f > 0) {
         excess_border[i] += (T)f;

@@ -453,11 +453,15 @@ __global__ void __launch_bounds__(TILE_VOX) k_count_active_tiles(Lattice L, Tile
 template <typename T>
 __global__ void k_slab_unpack_tiles(Lattice L, Tiles TL, State<T> S, int z_ghost, int z_border, int k_border_to_ghost,
                                     const int* __restrict__ h_in, const double* __restrict__ f_in,
-                                    int* __restrict__ rflag, WorkList rl, int* __restrict__ pflag, WorkList pl0, WorkList pl1,
+                                    int* __restrict__ rflag, WorkList rl0, WorkList rl1, const int* __restrict__ rl_cur_dev,
+                                    int rl_cur_host, int* __restrict__ pflag, WorkList pl0, WorkList pl1,
                                     int* __restrict__ changed)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= L.plane) return;
+    // the relabel list consumed next: device-resident selector when the BFS runs as a cooperative kernel
+    const int rc = rl_cur_dev ? *rl_cur_dev : rl_cur_host;
+    const WorkList rl = rc ? rl1 : rl0;
     const int y = (int)(i / L.stride[1]), x = (int)(i % L.stride[1]);
     const unsigned vg = (unsigned)z_ghost * L.plane + i, vb = (unsigned)z_border * L.plane + i;
     const int tg = ((z_ghost / TILE) * TL.nt[1] + y / TILE) * TL.nt[2] + x / TILE;
@@ -465,7 +469,7 @@ __global__ void k_slab_unpack_tiles(Lattice L, Tiles TL, State<T> S, int z_ghost
     const int hn = h_in[i];
     if (S.height[vg] != hn) {
         S.height[vg] = hn;
-        *changed = 1;
+        if (changed) *changed = 1;
         list_push(rflag, rl, tb);
         if (tg != tb) list_push(rflag, rl, tg);
     }

@@ -70,6 +70,8 @@ class SlabSolver:
         self.msg_bytes = self.h_bytes + self.plane * 8
         mk = lambda: torch.zeros(self.msg_bytes, dtype=torch.uint8, device=self.tdev)
         self.send_lo, self.send_hi, self.recv_lo, self.recv_hi = mk(), mk(), mk(), mk()
+        self.flag = torch.zeros(1, dtype=torch.int32, device=self.tdev)     # "a ghost label changed", set by unpack
+        self.count = torch.zeros(1, dtype=torch.int64, device=self.tdev)    # active voxels, written by the handle
         self.passes0, self.passes_max = int(passes0), int(passes_max)
         self.stats = {"exchanges": 0, "relabel_rounds": 0, "global_relabels": 0, "push_passes": 0}
 
@@ -108,8 +110,9 @@ class SlabSolver:
     def _ptr(self, t):
         return t.data_ptr() if self.native else t
 
-    def exchange(self):
-        """pack -> send/recv with both neighbours -> unpack.  Returns 1 if a ghost label changed here."""
+    def exchange(self, want_changed=False):
+        """pack -> send/recv with both neighbours -> unpack; everything is enqueued on the stream, the host never
+        waits.  With ``want_changed`` the unpack kernel raises ``self.flag`` (device) if a ghost label changed."""
         torch, dist = self.torch, self.dist
         hl, fl = self._views(self.send_lo)
         hh, fh = self._views(self.send_hi)
@@ -127,10 +130,10 @@ class SlabSolver:
                 req.wait()
         rhl, rfl = self._views(self.recv_lo)
         rhh, rfh = self._views(self.recv_hi)
-        changed = self.handle.slab_unpack(self._ptr(rhl) if self.ghost_lo else 0, self._ptr(rfl) if self.ghost_lo else 0,
-                                          self._ptr(rhh) if self.ghost_hi else 0, self._ptr(rfh) if self.ghost_hi else 0)
+        self.handle.slab_unpack(self._ptr(rhl) if self.ghost_lo else 0, self._ptr(rfl) if self.ghost_lo else 0,
+                                self._ptr(rhh) if self.ghost_hi else 0, self._ptr(rfh) if self.ghost_hi else 0,
+                                self._ptr(self.flag) if want_changed else 0)
         self.stats["exchanges"] += 1
-        return int(changed)
 
     def _allreduce(self, value, op):
         t = self.torch.tensor([value], dtype=self.torch.int64, device=self.tdev)
@@ -143,12 +146,22 @@ class SlabSolver:
         dist = self.dist
         self.handle.slab_relabel_begin()
         while True:
-            self.handle.slab_relabel_relax()
-            changed = self.exchange()
+            self.handle.slab_relabel_relax(False)
+            self.flag.zero_()
+            self.exchange(want_changed=True)
             self.stats["relabel_rounds"] += 1
-            if self.world == 1 or self._allreduce(changed, dist.ReduceOp.MAX) == 0:
+            if self.world > 1:
+                dist.all_reduce(self.flag, op=dist.ReduceOp.MAX, group=self.group)
+            if int(self.flag.item()) == 0:          # the one host synchronisation of the round
                 break
         self.stats["global_relabels"] += 1
+
+    def active(self):
+        """Global number of active voxels (device counters all-reduced; one host synchronisation)."""
+        self.handle.slab_count_active_dev(self._ptr(self.count))
+        if self.world > 1:
+            self.dist.all_reduce(self.count, op=self.dist.ReduceOp.SUM, group=self.group)
+        return int(self.count.item())
 
     def solve(self, max_rounds=100000):
         """Run to a maximum preflow.  Returns this rank's energy share; use ``energy()`` for the total."""
@@ -158,8 +171,7 @@ class SlabSolver:
         rounds = 0
         while True:
             self.global_relabel()
-            active = self._allreduce(int(self.handle.slab_count_active()), dist.ReduceOp.SUM)
-            if active == 0:
+            if self.active() == 0:
                 break
             rounds += 1
             if rounds > max_rounds:

@@ -94,7 +94,7 @@ class FakeSlab:
     def slab_relabel_begin(self):
         self.height = numpy.where(self.owned & (self._sinkres() > 0), 1, HINF).astype(numpy.int64)
 
-    def slab_relabel_relax(self):
+    def slab_relabel_relax(self, want_changed=False):
         any_change = False
         while True:
             best = self.height.copy()
@@ -158,7 +158,10 @@ class FakeSlab:
             f_hi.numpy()[:] = self.excess[self.own1].ravel()
             self.excess[self.own1] = 0
 
-    def slab_unpack(self, h_lo, f_lo, h_hi, f_hi):
+    def slab_count_active_dev(self, out):
+        out.numpy()[0] = self.slab_count_active()
+
+    def slab_unpack(self, h_lo, f_lo, h_hi, f_hi, changed_out=0):
         changed = 0
         psh = self.shape[1:]
         if self.glo and not isinstance(h_lo, int):
@@ -177,6 +180,8 @@ class FakeSlab:
             f = f_hi.numpy().reshape(psh)
             self.excess[self.own1 - 1] += f
             self.cap[1][self.own1 - 1] += f
+        if changed and not isinstance(changed_out, int):
+            changed_out.numpy()[0] = 1
         return changed
 
     def slab_finish(self):

@@ -372,15 +372,20 @@ def _two_slabs_one_gpu(vol, regional, split):
     mk = lambda dt: torch.zeros(P, dtype=dt, device="cuda")
     # message buffers: rank 0's upper side <-> rank 1's lower side
     s0h, s0f, s1h, s1f = mk(torch.int32), mk(torch.float64), mk(torch.int32), mk(torch.float64)
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
 
     def exchange():
+        flag.zero_()
+        torch.cuda.synchronize()
         hs[0].slab_pack(0, 0, s0h.data_ptr(), s0f.data_ptr())
         hs[1].slab_pack(s1h.data_ptr(), s1f.data_ptr(), 0, 0)
         for h in hs:
             h.synchronize()
-        c0 = hs[0].slab_unpack(0, 0, s1h.data_ptr(), s1f.data_ptr())
-        c1 = hs[1].slab_unpack(s0h.data_ptr(), s0f.data_ptr(), 0, 0)
-        return c0 or c1
+        hs[0].slab_unpack(0, 0, s1h.data_ptr(), s1f.data_ptr(), flag.data_ptr())
+        hs[1].slab_unpack(s0h.data_ptr(), s0f.data_ptr(), 0, 0, flag.data_ptr())
+        for h in hs:
+            h.synchronize()
+        return int(flag.item())
 
     passes, rounds = 1, 0
     while True:
@@ -388,7 +393,7 @@ def _two_slabs_one_gpu(vol, regional, split):
             h.slab_relabel_begin()
         while True:
             for h in hs:
-                h.slab_relabel_relax()
+                h.slab_relabel_relax(False)
             if not exchange():
                 break
         if sum(h.slab_count_active() for h in hs) == 0:
