@@ -92,6 +92,7 @@ typedef struct mgc_stats {
     double ms_push;             /* device ms inside push/relabel sweeps (CUDA events around each batch)  */
     double ms_relabel;          /* device ms inside global-relabel kernels (init + relaxation sweeps)    */
     double ms_boundary;         /* device ms of the last boundary (n-link) kernel alone                  */
+    double ms_init;             /* device ms of the solver-state initialisation kernel (k_init_tile)     */
 } mgc_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------- */

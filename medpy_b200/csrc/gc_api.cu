@@ -129,6 +129,7 @@ struct mgc_graph {
     cudaEvent_t ev_terms[2] = {};      // span of the term kernels since the last reset
     bool terms_open = false;
 
+    bool init_timed = false;           // ev[4..5] bracket the last k_init_tile
     bool caps_fresh = true;            // capacity arrays not written yet since create/reset (hold garbage)
     bool tr_fresh = true;              // same for tr[]
     bool state_init = false;
@@ -154,7 +155,7 @@ struct mgc_graph {
     int coop_bfs_grid = 0;             // co-resident CTAs of k_bfs_coop (0: per-pass host loop)
     int coop_grid = 0;                 // co-resident CTAs of k_solve_coop
     int tile_iters = 8;                // synchronous push/relabel rounds per tile visit
-    int passes0 = 1, passes_max = 8;   // two-colour passes per round: starts at passes0, doubles up to passes_max
+    int passes0 = 1, passes_max = 32;  // two-colour passes per round: starts at passes0, at most doubles per round
 
     // tuning
     int sweeps_per_round = 32;
@@ -614,8 +615,11 @@ int init_tiles(mgc_graph* g)
 {
     CK(cudaMemsetAsync(g->d_tcount, 0, 256, g->stream));
     g->pl_sel[0] = g->pl_sel[1] = 0;
+    cudaEventRecord(g->ev[4], g->stream);
     k_init_tile<double><<<g->TL.ntiles, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S, g->rflag, rl(g, 0), g->pflag,
                                                                   pl(g, 0, 0), pl(g, 1, 0));
+    cudaEventRecord(g->ev[5], g->stream);
+    g->init_timed = true;
     g->st.kernel_launches++;
     CK(cudaGetLastError());
     g->state_init = true;
@@ -800,16 +804,25 @@ int solve_tiles(mgc_graph* g)
     int passes = g->passes0;
     int64_t rounds = 0;
     for (;;) {
+        const double rel0 = g->st.ms_relabel;
         rc = relabel_tiles(g);
         if (rc) return rc;
+        const double t_rel = g->st.ms_relabel - rel0;
         int64_t active = 0;
         rc = count_active_tiles(g, &active);
         if (rc) return rc;
         if (active == 0) break;
         if (++rounds > g->max_rounds) FAIL(MGC_E_NOCONV, "push-relabel did not converge within the round cap");
+        const double push0 = g->st.ms_push;
         rc = push_tiles(g, passes);
         if (rc) return rc;
-        passes = passes * 2 > g->passes_max ? g->passes_max : passes * 2;
+        // next round: at most double, and no more push time than one global relabel costs (measured, not guessed):
+        // easy instances keep relabelling often, hard ones (long BFS, cheap passes) push longer between relabels
+        const double t_pass = (g->st.ms_push - push0) / passes;
+        int want = t_pass > 1e-4 ? (int)(t_rel / t_pass + 0.999) : passes * 2;
+        if (want < 1) want = 1;
+        if (want > passes * 2) want = passes * 2;
+        passes = want > g->passes_max ? g->passes_max : want;
     }
     return MGC_OK;
 }
@@ -825,6 +838,11 @@ int readout(mgc_graph* g, double* energy_part)
     CK(cudaStreamSynchronize(g->stream));
     g->st.flow_const = sc[0];
     *energy_part = sc[0] + sc[1];
+    if (g->init_timed) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, g->ev[4], g->ev[5]) == cudaSuccess) g->st.ms_init = ms;
+        g->init_timed = false;
+    }
     return MGC_OK;
 }
 
@@ -1008,6 +1026,7 @@ int mgc_add_boundary(mgc_graph* g, int32_t kind, const mgc_array* image, double 
     // boundary_maximum_division computes the difference variant (energy_voxel.py:347)
     P.use_max = (kind >= 4 && kind != MGC_BOUNDARY_MAXIMUM_DIVISION) ? 1 : 0;
     P.sigma = (P.fn == 1) ? pow(sigma, 2) : sigma;   // math.pow(sigma, 2), energy_voxel.py:231
+    P.inv_sigma2 = (P.fn == 1 && P.sigma != 0.0) ? 1.0 / P.sigma : 0.0;
     P.inv_spacing_on = spacing ? 1.0 : 0.0;
     for (int d = 0; d < 4; ++d) P.spacing[d] = 1.0;
     if (spacing) for (int d = 0; d < g->user_ndim; ++d) P.spacing[d + g->shift] = spacing[d];

@@ -201,7 +201,7 @@ public:
         d["n_voxels"] = s.n_voxels; d["push_sweeps"] = s.push_sweeps; d["global_relabels"] = s.global_relabels;
         d["relabel_sweeps"] = s.relabel_sweeps; d["kernel_launches"] = s.kernel_launches; d["active_last"] = s.active_last;
         d["ms_terms"] = s.ms_terms; d["ms_solve"] = s.ms_solve; d["ms_readout"] = s.ms_readout;
-        d["ms_push"] = s.ms_push; d["ms_relabel"] = s.ms_relabel; d["ms_boundary"] = s.ms_boundary;
+        d["ms_push"] = s.ms_push; d["ms_relabel"] = s.ms_relabel; d["ms_boundary"] = s.ms_boundary; d["ms_init"] = s.ms_init;
         d["flow_const"] = s.flow_const; d["energy"] = s.energy; d["device_bytes"] = s.device_bytes;
         return d;
     }

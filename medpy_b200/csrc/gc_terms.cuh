@@ -114,6 +114,7 @@ struct BoundaryParams {
     int use_max;       // 1: g(max(|a|,|b|)) (energy_voxel.py:519-558), 0: g(|a-b|) (:561-608)
     double norm;       // linear: M
     double sigma;      // division / power: sigma ; exponential: pow(sigma, 2)
+    double inv_sigma2; // exponential: 1 / pow(sigma, 2) (see g_weight)
     double inv_spacing_on; // 0: no spacing
     double spacing[4]; // canonical axes
 };
@@ -125,7 +126,12 @@ __device__ __forceinline__ double g_weight(const BoundaryParams& P, double x)
         w = __dsub_rn(1.0, __ddiv_rn(x, P.norm));
         if (w == 0.0) w = DBL_MIN;
     } else if (P.fn == 1) {                // :226-236,290-300
-        double t = __ddiv_rn(__dmul_rn(x, x), P.sigma);
+        // x^2 / sigma^2 as a multiplication by the pre-computed reciprocal: K1 is instruction-issue bound (fp64 exp
+        // + IEEE division, profiles/r01_*), and exp() is not bit-identical to numpy's libm anyway; the argument moves
+        // by <= 1 ulp, i.e. the weight by <= |arg| * 1.1e-16 relative (tests allow 2e-13; the north star 1e-5).
+        // sigma == 0 keeps the exact division so x = 0 still gives NaN and x > 0 gives DBL_MIN like the reference.
+        double t = (P.inv_sigma2 > 0.0 && P.inv_sigma2 < 1e300) ? __dmul_rn(__dmul_rn(x, x), P.inv_sigma2)
+                                                                : __ddiv_rn(__dmul_rn(x, x), P.sigma);
         w = exp(-t);
         if (w <= 0.0) w = DBL_MIN;
     } else if (P.fn == 2) {                // :337-345,399-407

@@ -71,7 +71,7 @@ def test_golden_case(name):
         if exact:
             assert numpy.array_equal(w, ref, equal_nan=True)
         else:
-            numpy.testing.assert_allclose(w, ref, rtol=1e-15 * 4, atol=0)
+            numpy.testing.assert_allclose(w, ref, rtol=2e-13, atol=0)
         assert numpy.array_equal(w, wr, equal_nan=True)  # symmetric arcs (energy_voxel.py:664)
     tr = numpy.asarray([g.get_trcap(p) for p in range(min(n, 600))])
     assert numpy.array_equal(tr, c["tr"][: tr.size])
