@@ -7,6 +7,7 @@
 #include "gc_solver.cuh"
 #include "gc_tiles.cuh"
 #include "gc_persist.cuh"
+#include "gc_tma.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -153,6 +154,8 @@ struct mgc_graph {
     int n_ctas = 296;                  // persistent CTAs per tile-kernel launch
     bool use_coop = false;             // whole solve as one cooperative launch (gc_persist.cuh); opt-in, MEDPY_GC_COOP=1
     int coop_bfs_grid = 0;             // co-resident CTAs of k_bfs_coop (0: per-pass host loop)
+    bool use_tma = false;              // push kernel stages its tile planes with TMA (gc_tma.cuh)
+    PushMaps maps{};                   // tensor maps of cap[0..5] and excess
     int coop_grid = 0;                 // co-resident CTAs of k_solve_coop
     int tile_iters = 8;                // synchronous push/relabel rounds per tile visit
     int passes0 = 1, passes_max = 32;  // two-colour passes per round: starts at passes0, at most doubles per round
@@ -349,6 +352,39 @@ void resolve_term_span(mgc_graph* g)
     g->terms_open = false;
 }
 
+// rank-3 float64 tensor maps with an 8x8x8 box over the local lattice (x fastest); driver entry point resolved at run
+// time so the library does not link libcuda
+bool make_push_maps(mgc_graph* g)
+{
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+            cudaGetLastError();
+            return false;
+        }
+        encode = (encode_fn)fn;
+    }
+    const cuuint64_t X = (cuuint64_t)g->L.dim[2], Y = (cuuint64_t)g->L.dim[1], Z = (cuuint64_t)g->L.dim[0];
+    if (X % 2) return false;                                   // global strides must be multiples of 16 B
+    const cuuint64_t dims[3] = {X, Y, Z};
+    const cuuint64_t strides[2] = {X * 8, X * Y * 8};
+    const cuuint32_t box[3] = {TILE, TILE, TILE};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    for (int p = 0; p < TMA_PLANES; ++p) {
+        void* base = p < 6 ? (void*)g->S.cap[p] : (void*)g->S.excess;
+        if (((uintptr_t)base) & 15) return false;
+        if (encode(&g->maps.m[p], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    return true;
+}
+
 int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool slab, int32_t device, mgc_graph** out)
 {
     if (!out) return MGC_E_ARG;
@@ -435,6 +471,15 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
         if (const char* e2 = getenv("MEDPY_GC_PASSES0")) if (atoi(e2) > 0) g->passes0 = atoi(e2);
         if (const char* e3 = getenv("MEDPY_GC_PASSES_MAX")) if (atoi(e3) > 0) g->passes_max = atoi(e3);
         if (const char* e4 = getenv("MEDPY_GC_COOP")) g->use_coop = atoi(e4) != 0;
+        {
+            const char* e6 = getenv("MEDPY_GC_TMA");
+            const size_t smem = 2 * TMA_STAGE_BYTES + 6 * TILE_VOX * sizeof(double) + 1024 * sizeof(int) + 64;
+            if ((!e6 || atoi(e6) != 0) && make_push_maps(g) &&
+                cudaFuncSetAttribute(k_push_tile_tma<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess)
+                g->use_tma = true;
+            else
+                cudaGetLastError();
+        }
         {
             int coop = 0, nb = 0;
             const char* e5 = getenv("MEDPY_GC_BFS");
@@ -715,6 +760,12 @@ int push_color(mgc_graph* g, int color)
 {
     const int a = g->pl_sel[color], oa = g->pl_sel[1 - color];
     CK(cudaMemsetAsync(cursor(g), 0, sizeof(int), g->stream));
+    if (g->use_tma) {
+        const size_t smem = 2 * TMA_STAGE_BYTES + 6 * TILE_VOX * sizeof(double) + 1024 * sizeof(int) + 64;
+        k_push_tile_tma<double><<<g->n_ctas, TILE_VOX, smem, g->stream>>>(g->L, g->TL, g->S, g->maps, g->tile_iters, g->pflag,
+                                                                          pl(g, color, a), cursor(g), pl(g, color, 1 - a),
+                                                                          pl(g, 1 - color, oa));
+    } else
     k_push_tile<double><<<g->n_ctas, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S, g->tile_iters, g->pflag, pl(g, color, a),
                                                                cursor(g), pl(g, color, 1 - a), pl(g, 1 - color, oa));
     CK(cudaMemsetAsync(g->d_tcount + 2 + color * 2 + a, 0, sizeof(int), g->stream));   // consumed list is empty again

@@ -335,10 +335,12 @@ __device__ __forceinline__ void pull_dir(const TileCtx& c, const T* s_out, T& e,
 }
 
 // one push/relabel discharge visit of tile t.  s_out = 6*TILE_VOX values, s_h = HALO_VOX ints of shared memory.
+// `stg` (optional): the tile's six capacity planes + excess already staged in shared memory by TMA (gc_tma.cuh),
+// plane p at stg + p * TILE_VOX, voxel order == thread order; nullptr = load from global memory here.
 template <typename T>
-__device__ __forceinline__ void push_visit(const Lattice& L, const Tiles& TL, const State<T>& S, int iters,
-                                           int* __restrict__ pflag, const WorkList& self_next, const WorkList& other_next,
-                                           int t, T* s_out, int* s_h)
+__device__ __forceinline__ void push_visit_staged(const Lattice& L, const Tiles& TL, const State<T>& S, int iters,
+                                                  int* __restrict__ pflag, const WorkList& self_next, const WorkList& other_next,
+                                                  int t, T* s_out, int* s_h, const double* stg)
 {
     const TileCtx c = tile_ctx(L, TL, t);
     const int tid = threadIdx.x;
@@ -347,9 +349,15 @@ __device__ __forceinline__ void push_visit(const Lattice& L, const Tiles& TL, co
     const int h0 = load_heights(L, c, S.height, s_h);
     T e = 0, scap = 0, sf = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
     if (c.inb) {
-        e = S.excess[c.v];
-        c0 = S.cap[0][c.v]; c1 = S.cap[1][c.v]; c2 = S.cap[2][c.v];
-        c3 = S.cap[3][c.v]; c4 = S.cap[4][c.v]; c5 = S.cap[5][c.v];
+        if (stg) {
+            c0 = (T)stg[0 * TILE_VOX + tid]; c1 = (T)stg[1 * TILE_VOX + tid]; c2 = (T)stg[2 * TILE_VOX + tid];
+            c3 = (T)stg[3 * TILE_VOX + tid]; c4 = (T)stg[4 * TILE_VOX + tid]; c5 = (T)stg[5 * TILE_VOX + tid];
+            e = (T)stg[6 * TILE_VOX + tid];
+        } else {
+            e = S.excess[c.v];
+            c0 = S.cap[0][c.v]; c1 = S.cap[1][c.v]; c2 = S.cap[2][c.v];
+            c3 = S.cap[3][c.v]; c4 = S.cap[4][c.v]; c5 = S.cap[5][c.v];
+        }
         const T tr = S.tr[c.v];
         if (tr < 0) { scap = -tr; sf = S.sink[c.v]; }
     }
@@ -407,6 +415,14 @@ __device__ __forceinline__ void push_visit(const Lattice& L, const Tiles& TL, co
     }
     const int still = (c.own && e > 0 && h < MGC_HINF) ? 1 : 0;
     if (__syncthreads_or(still) && tid == 0) list_push(pflag, self_next, t);
+}
+
+template <typename T>
+__device__ __forceinline__ void push_visit(const Lattice& L, const Tiles& TL, const State<T>& S, int iters,
+                                           int* __restrict__ pflag, const WorkList& self_next, const WorkList& other_next,
+                                           int t, T* s_out, int* s_h)
+{
+    push_visit_staged<T>(L, TL, S, iters, pflag, self_next, other_next, t, s_out, s_h, nullptr);
 }
 
 template <typename T>
