@@ -86,7 +86,7 @@ def regional_probability_map(graph, xxx_todo_changeme):
     snk_dtype = ((1 - probability_map[:0]) * alpha).dtype
     pure32 = probability_map.dtype == numpy.float32 and src_dtype == numpy.float32 and snk_dtype == numpy.float32
     pure64 = probability_map.dtype == numpy.float64 and src_dtype == numpy.float64 and snk_dtype == numpy.float64
-    if (pure32 or pure64) and all(s > 0 for s in probability_map.strides):
+    if pure32 or pure64:
         graph._add_regional_probability(probability_map, float(alpha), bool(pure32))
     else:
         # unusual dtype mixes: form the products with numpy exactly as the reference does, upload densely

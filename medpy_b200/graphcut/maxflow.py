@@ -130,7 +130,7 @@ class GraphDouble:
     def add_regional_probability(self, prob, alpha, compute_f32):
         self._flush()
         self._dirty()
-        self._nat().add_regional_probability(prob, float(alpha), bool(compute_f32))
+        self._nat().add_regional_probability(self._positive_strides(prob), float(alpha), bool(compute_f32))
 
     def add_tweights_dense(self, src, snk):
         self._flush()
@@ -139,15 +139,25 @@ class GraphDouble:
         snk = numpy.ascontiguousarray(snk, dtype=numpy.float64).reshape(self._shape)
         self._nat().add_tweights_dense(src, snk)
 
+    @staticmethod
+    def _positive_strides(a):
+        """Host arrays with zero / negative strides (broadcast views, reversed slices) are copied once; everything
+        else -- including Fortran-ordered arrays as medpy.io.load returns them -- is handed over as is."""
+        if a is None or not isinstance(a, numpy.ndarray):
+            return a
+        if any(st <= 0 and n > 1 for st, n in zip(a.strides, a.shape)):
+            return numpy.ascontiguousarray(a)
+        return a
+
     def add_markers(self, fg, bg):
         self._flush()
         self._dirty()
-        self._nat().add_markers(fg, bg)
+        self._nat().add_markers(self._positive_strides(fg), self._positive_strides(bg))
 
     def add_boundary(self, kind, image, sigma, spacing, norm):
         self._flush()
         self._dirty()
-        self._nat().add_boundary(int(kind), image, float(sigma), spacing, float(norm))
+        self._nat().add_boundary(int(kind), self._positive_strides(image), float(sigma), spacing, float(norm))
 
     def add_nweights_dense(self, axis, fwd, bwd):
         self._flush()

@@ -448,3 +448,105 @@ def test_multi_gpu_nccl_slabs_vs_oracle(tmp_path, case):
     oflow, omask, _ = _oracle_solve(prob)
     assert numpy.array_equal(got["mask"], omask)
     assert abs(float(got["energy"]) - oflow) <= 1e-9 * abs(oflow)
+
+
+# ------------------------------------------------------------------------------------------------------
+# edge cases (SURVEY.md §4 "gaps the new repo must fill itself")
+# ------------------------------------------------------------------------------------------------------
+def _solve_both(fg, bg, regional=None, boundary=None):
+    """(our flow, our mask, oracle flow, oracle mask) for one problem given in oracle.build_problem's terms."""
+    from oracle import energy_terms as et
+    gc = _gc()
+    kw = {}
+    if boundary is not None:
+        kind, img, sigma, spacing = boundary
+        fn = getattr(gc.energy_voxel, "boundary_" + kind)
+        kw.update(boundary_term=fn, boundary_term_args=(img, spacing) if kind.endswith("linear") else (img, sigma, spacing))
+    if regional is not None:
+        kw.update(regional_term=gc.energy_voxel.regional_probability_map, regional_term_args=regional)
+    g = gc.graph_from_voxels(fg, bg, **kw)
+    flow = g.maxflow()
+    assert g.maxflow() == flow          # Graph::maxflow may be called repeatedly (graph.h:129)
+    with numpy.errstate(all="ignore"):
+        prob = et.build_problem(fg, bg, regional=regional, boundary=boundary)
+    oflow, omask, _ = _oracle_solve(prob)
+    return flow, g.get_mask(), oflow, omask
+
+
+@pytest.mark.parametrize("shape", [(9, 7, 13), (1, 1, 37), (3, 17, 1), (8, 8, 8), (16, 9, 24), (5, 5, 5, 3)])
+def test_ragged_shapes_and_odd_extents(shape):
+    """Partial tiles, odd x extents (no TMA path), degenerate axes, 4-D."""
+    rng = numpy.random.default_rng(sum(shape))
+    img = (rng.normal(size=shape) * 20).astype(numpy.float32)
+    fg = rng.random(shape) < 0.06
+    bg = (rng.random(shape) < 0.06) & ~fg
+    f, m, of, om = _solve_both(fg, bg, regional=(rng.random(shape).astype(numpy.float32), 0.4),
+                               boundary=("difference_exponential", img, 12.0, False))
+    assert numpy.array_equal(m, om) and abs(f - of) <= 1e-9 * max(1.0, abs(of))
+
+
+def test_missing_marker_sets_and_empty_graph():
+    shape = (6, 7, 8)
+    rng = numpy.random.default_rng(1)
+    img = (rng.normal(size=shape) * 20).astype(numpy.float64)
+    z = numpy.zeros(shape, bool)
+    fg = z.copy(); fg[2, 3, 4] = True
+    bg = z.copy(); bg[0, 0, 0] = True
+    for f_, b_ in ((fg, z), (z, bg), (z, z)):
+        f, m, of, om = _solve_both(f_, b_, boundary=("difference_division", img, 3.0, False))
+        assert numpy.array_equal(m, om) and f == of
+    # nothing at all: no terms, no markers -> flow 0, every node free -> mask 1 (graph.h:560-571 default SOURCE)
+    g = _gc().graph_from_voxels(z, z)
+    assert g.maxflow() == 0.0 and g.get_mask().all()
+
+
+def test_strided_inputs_fortran_negative_and_broadcast():
+    """Fortran order (as medpy.io.load returns), reversed views and broadcast markers all describe the same logical
+    arrays as their contiguous copies (node ids are C-order over the LOGICAL shape, generate.py:170-172)."""
+    from medpy_b200 import synthetic
+    shape = (18, 20, 22)
+    vol = synthetic.two_blob_volume(shape, seed=6)
+    ref = _solve_both(vol["fg"], vol["bg"], regional=(vol["prob"], 0.1), boundary=("difference_exponential", vol["image"], vol["sigma"], False))
+    gc = _gc()
+    variants = [
+        dict(img=numpy.asfortranarray(vol["image"]), prob=numpy.asfortranarray(vol["prob"]), fg=numpy.asfortranarray(vol["fg"]), bg=numpy.asfortranarray(vol["bg"])),
+        dict(img=vol["image"][::-1][::-1], prob=numpy.ascontiguousarray(vol["prob"][:, ::-1])[:, ::-1], fg=vol["fg"], bg=vol["bg"]),
+        dict(img=vol["image"].astype(numpy.float64)[:, :, ::1], prob=vol["prob"], fg=vol["fg"].astype(numpy.uint8), bg=vol["bg"].astype(numpy.int64)),
+    ]
+    for v in variants:
+        g = gc.graph_from_voxels(v["fg"], v["bg"], regional_term=gc.energy_voxel.regional_probability_map,
+                                 regional_term_args=(v["prob"], 0.1), boundary_term=gc.energy_voxel.boundary_difference_exponential,
+                                 boundary_term_args=(v["img"], vol["sigma"], False))
+        assert g.maxflow() == ref[0]
+        assert numpy.array_equal(g.get_mask(), ref[1])
+    assert numpy.array_equal(ref[1], ref[3])
+
+
+def test_int16_maximum_terms_and_wraparound():
+    """maximum_* terms take numpy.abs in the INPUT dtype (energy_voxel.py:558): abs(-32768) wraps for int16."""
+    shape = (6, 6, 6)
+    rng = numpy.random.default_rng(3)
+    img = rng.integers(-300, 300, size=shape).astype(numpy.int16)
+    img[1, 1, 1] = -32768
+    fg = numpy.zeros(shape, bool); fg[2, 2, 2] = True
+    bg = numpy.zeros(shape, bool); bg[0] = True
+    for kind, sigma in (("maximum_exponential", 200.0), ("maximum_power", 0.5), ("difference_division", 50.0)):
+        f, m, of, om = _solve_both(fg, bg, boundary=(kind, img, sigma, (1.0, 2.0, 0.5)))
+        assert numpy.array_equal(m, om) and abs(f - of) <= 1e-9 * max(1.0, abs(of)), kind
+
+
+def test_reset_reuses_the_handle():
+    from medpy_b200 import synthetic
+    from medpy_b200.graphcut.device import graph_from_device_arrays
+    import torch
+    vol = synthetic.two_blob_volume((20, 20, 20), seed=8)
+    t = {k: torch.from_numpy(numpy.ascontiguousarray(vol[k])).cuda() for k in ("image", "prob")}
+    fg, bg = torch.from_numpy(vol["fg"]).cuda(), torch.from_numpy(vol["bg"]).cuda()
+    g = None
+    outs = []
+    for rep in range(3):
+        g = graph_from_device_arrays(fg, bg, image=t["image"], boundary="difference_exponential", sigma=vol["sigma"],
+                                     prob=t["prob"], alpha=0.1, graph=g)
+        outs.append((g.maxflow(), g.get_mask().copy()))
+    assert outs[0][0] == outs[1][0] == outs[2][0]
+    assert numpy.array_equal(outs[0][1], outs[2][1])
