@@ -8,6 +8,7 @@
 #include "gc_tiles.cuh"
 #include "gc_persist.cuh"
 #include "gc_tma.cuh"
+#include "gc_tiles4.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -142,6 +143,8 @@ struct mgc_graph {
 
     // tile solver (3-D lattices)
     Tiles TL{};
+    Tiles4 TL4{};                      // 4-D lattices: 4x4x8x4 tiles (gc_tiles4.cuh)
+    uint8_t* smask = nullptr;          // 4-D: residual sink link flag (the 8 arc bits fill rmask)
     bool use_tiles = false;
     int* pflag = nullptr;              // push: tile is already on the list its colour consumes next
     int* rflag = nullptr;              // relabel: tile is already on the next relabel list
@@ -502,6 +505,25 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
             }
         }
     }
+    if (!rc && g->nd == 4 && !slab) {
+        const int ext[4] = {4, 4, 8, 4};
+        g->TL4.ntiles = 1;
+        for (int d = 0; d < 4; ++d) { g->TL4.nt[d] = (g->L.dim[d] + ext[d] - 1) / ext[d]; g->TL4.ntiles *= g->TL4.nt[d]; }
+        g->TL.ntiles = g->TL4.ntiles;   // list sizes / shared helpers
+        const size_t tb = (size_t)g->TL4.ntiles * sizeof(int);
+        if (!rc) { rc = alloc_buf(g, tb, &p); g->pflag = (int*)p; }
+        if (!rc) { rc = alloc_buf(g, tb, &p); g->rflag = (int*)p; }
+        for (int i = 0; i < 2 && !rc; ++i) { rc = alloc_buf(g, tb, &p); g->rl_items[i] = (int*)p; }
+        for (int i = 0; i < 4 && !rc; ++i) { rc = alloc_buf(g, tb, &p); g->pl_items[i >> 1][i & 1] = (int*)p; }
+        if (!rc) { rc = alloc_buf(g, 256, &p); g->d_tcount = (int*)p; }
+        if (!rc) { rc = alloc_buf(g, nb, &p); g->smask = (uint8_t*)p; }
+        g->n_ctas = 2 * cached_sm_count(device);
+        g->use_tiles = true;
+        if (const char* sv = getenv("MEDPY_GC_SOLVER")) if (!strcmp(sv, "v0")) g->use_tiles = false;
+        if (const char* e1 = getenv("MEDPY_GC_ITERS")) if (atoi(e1) > 0) g->tile_iters = atoi(e1);
+        if (const char* e2 = getenv("MEDPY_GC_PASSES0")) if (atoi(e2) > 0) g->passes0 = atoi(e2);
+        if (const char* e3 = getenv("MEDPY_GC_PASSES_MAX")) if (atoi(e3) > 0) g->passes_max = atoi(e3);
+    }
     if (rc) { g_create_error = g->err; mgc_destroy(g); return rc; }
     if (cudaStreamCreate(&g->stream) != cudaSuccess) { g_create_error = "cudaStreamCreate failed"; mgc_destroy(g); return MGC_E_CUDA; }
     g->own_stream = true;
@@ -661,6 +683,10 @@ int init_tiles(mgc_graph* g)
     CK(cudaMemsetAsync(g->d_tcount, 0, 256, g->stream));
     g->pl_sel[0] = g->pl_sel[1] = 0;
     cudaEventRecord(g->ev[4], g->stream);
+    if (g->nd == 4)
+        k_init_tile4<double><<<g->TL4.ntiles, T4_VOX, 0, g->stream>>>(g->L, g->TL4, g->S, g->smask, g->rflag, rl(g, 0), g->pflag,
+                                                                      pl(g, 0, 0), pl(g, 1, 0));
+    else
     k_init_tile<double><<<g->TL.ntiles, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S, g->rflag, rl(g, 0), g->pflag,
                                                                   pl(g, 0, 0), pl(g, 1, 0));
     cudaEventRecord(g->ev[5], g->stream);
@@ -685,7 +711,9 @@ int relabel_tiles_begin(mgc_graph* g)
     }
     CK(cudaMemsetAsync(g->d_tcount, 0, 2 * sizeof(int), g->stream));
     CK(cudaMemsetAsync(g->rflag, 0, (size_t)g->TL.ntiles * sizeof(int), g->stream));
-    {
+    if (g->nd == 4) {
+        k_relabel_reset4<<<g->TL4.ntiles, T4_VOX, 0, g->stream>>>(g->L, g->TL4, g->S.rmask, g->smask, g->S.height, g->rflag, rl(g, 0));
+    } else {
         const unsigned nruns = (unsigned)g->L.dim[0] * (unsigned)g->L.dim[1] * (unsigned)g->TL.nt[2];
         unsigned grid = (nruns + 255u) / 256u;
         if (grid > (unsigned)g->n_ctas * 8u) grid = (unsigned)g->n_ctas * 8u;
@@ -702,7 +730,7 @@ int relabel_tiles_begin(mgc_graph* g)
 int relabel_tiles_run(mgc_graph* g, int* any, bool want_any = true)
 {
     *any = 0;
-    if (g->coop_bfs_grid > 0) {
+    if (g->coop_bfs_grid > 0 && g->nd == 3) {
         // all passes in one cooperative launch; the list selector lives in the control block (device side), so the
         // host does not have to synchronise unless the caller wants to know whether anything moved
         CK(cudaMemsetAsync(g->d_tcount + CTL_CURSOR, 0, sizeof(int), g->stream));
@@ -729,6 +757,10 @@ int relabel_tiles_run(mgc_graph* g, int* any, bool want_any = true)
         CK(cudaMemsetAsync(g->d_tcount + (1 - cur), 0, sizeof(int), g->stream));
         CK(cudaMemsetAsync(cursor(g), 0, sizeof(int), g->stream));
         const int grid = pending < g->n_ctas * 2 ? pending : g->n_ctas * 2;   // 4 KB smem: more CTAs per SM fit
+        if (g->nd == 4)
+            k_relabel_tile4<<<grid, T4_VOX, 0, g->stream>>>(g->L, g->TL4, g->S.rmask, g->S.height, g->rflag, rl(g, cur),
+                                                            cursor(g), rl(g, 1 - cur));
+        else
         k_relabel_tile<<<grid, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S.rmask, g->S.height, g->rflag, rl(g, cur),
                                                          cursor(g), rl(g, 1 - cur));
         g->rl_cur = 1 - cur;
@@ -760,7 +792,10 @@ int push_color(mgc_graph* g, int color)
 {
     const int a = g->pl_sel[color], oa = g->pl_sel[1 - color];
     CK(cudaMemsetAsync(cursor(g), 0, sizeof(int), g->stream));
-    if (g->use_tma) {
+    if (g->nd == 4) {
+        k_push_tile4<double><<<g->n_ctas, T4_VOX, 0, g->stream>>>(g->L, g->TL4, g->S, g->smask, g->tile_iters, g->pflag, pl(g, color, a),
+                                                                  cursor(g), pl(g, color, 1 - a), pl(g, 1 - color, oa));
+    } else if (g->use_tma) {
         const size_t smem = 2 * TMA_STAGE_BYTES + 6 * TILE_VOX * sizeof(double) + 1024 * sizeof(int) + 64;
         k_push_tile_tma<double><<<g->n_ctas, TILE_VOX, smem, g->stream>>>(g->L, g->TL, g->S, g->maps, g->tile_iters, g->pflag,
                                                                           pl(g, color, a), cursor(g), pl(g, color, 1 - a),
@@ -796,8 +831,12 @@ int push_tiles(mgc_graph* g, int passes)
 int count_active_tiles(mgc_graph* g, int64_t* out)
 {
     CK(cudaMemsetAsync(g->d_count, 0, sizeof(unsigned long long), g->stream));
-    for (int color = 0; color < 2; ++color)
-        k_count_active_tiles<double><<<g->n_ctas * 2, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S, pl(g, color, g->pl_sel[color]), g->d_count);
+    for (int color = 0; color < 2; ++color) {
+        if (g->nd == 4)
+            k_count_active_tiles4<double><<<g->n_ctas * 2, T4_VOX, 0, g->stream>>>(g->L, g->TL4, g->S, pl(g, color, g->pl_sel[color]), g->d_count);
+        else
+            k_count_active_tiles<double><<<g->n_ctas * 2, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S, pl(g, color, g->pl_sel[color]), g->d_count);
+    }
     g->st.kernel_launches += 2;
     unsigned long long c = 0;
     CK(cudaMemcpyAsync(&c, g->d_count, sizeof(c), cudaMemcpyDeviceToHost, g->stream));
@@ -847,7 +886,7 @@ int solve_tiles(mgc_graph* g)
         rc = init_tiles(g);
         if (rc) return rc;
     }
-    if (g->use_coop) {
+    if (g->use_coop && g->nd == 3) {
         const int flags = SOLVE_F_LOOP | (g->labels_fresh ? 0 : SOLVE_F_RESET);
         g->labels_fresh = false;
         return solve_coop(g, flags, g->passes0, nullptr);

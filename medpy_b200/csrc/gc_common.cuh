@@ -14,6 +14,12 @@
 
 #define MGC_HINF 0x3fffffff
 #define MGC_MAXDIR 8
+// The source link of a voxel is clamped to what can leave it: sum of its out-capacities (rounded up) times this slack.
+// The slack matters: the excess is consumed by a SEQUENCE of rounded subtractions (one per saturated arc, in whatever
+// order the solver visits them), and without head-room the last arc can be left with a one-ulp residual that keeps
+// the voxel "connected to the sink" although every arc is saturated in exact arithmetic (found by the full-size 512^3
+// comparison against BK: 1 voxel of 134 M, tools/compare_fullsize.py).  Any factor > 1 + a few ulp is correct.
+#define SOURCE_CLAMP_SLACK 1.0000001
 
 struct Lattice {
     int nd;                 // canonical number of axes: 3 or 4

@@ -25,7 +25,8 @@ __global__ void __launch_bounds__(256) k_init_state(Lattice L, State<T> S)
         double out = 0.0;
 #pragma unroll
         for (int k = 0; k < 2 * ND; ++k) out = __dadd_ru(out, (double)S.cap[k][v]);
-        e = tr < out ? tr : out;
+        const double lim = out * SOURCE_CLAMP_SLACK;
+        e = tr < lim ? tr : lim;
         if (!(out == out)) e = tr;  // NaN capacities (zero-image linear terms): leave the link alone
     }
     if (!owned(L, v)) e = 0.0;      // ghost planes of a z-slab start with an empty outbox

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(TILE_VOX) k_init_tile(Lattice L, Tiles TL, Sta
             out = __dadd_ru(out, ck);
         }
         double e = 0.0;
-        if (tr > 0) { e = tr < out ? tr : out; if (!(out == out)) e = tr; }
+        if (tr > 0) { const double lim = out * SOURCE_CLAMP_SLACK; e = tr < lim ? tr : lim; if (!(out == out)) e = tr; }
         if (tr < 0) m |= RM_SINK;
         if (!c.own) e = 0.0;
         S.excess[c.v] = (T)e;

@@ -550,3 +550,40 @@ def test_reset_reuses_the_handle():
         outs.append((g.maxflow(), g.get_mask().copy()))
     assert outs[0][0] == outs[1][0] == outs[2][0]
     assert numpy.array_equal(outs[0][1], outs[2][1])
+
+
+def test_source_clamp_leaves_no_one_ulp_residuals():
+    """Regression (found by the full-size 512^3 comparison with BK, tools/compare_fullsize.py): a strongly source-linked
+    voxel whose out-capacities are all tiny must end up cut off from its sink-side neighbours with EVERY arc saturated.
+    The solver clamps the source link to the sum of the out-capacities; without head-room the sequence of rounded
+    subtractions could leave a one-ulp residual on the last arc and the voxel stayed "connected to the sink".
+    4096 such voxels with random capacities, all other voxels sink-linked."""
+    from oracle import energy_terms as et
+    gc = _gc()
+    rng = numpy.random.default_rng(123)
+    shape = (33, 33, 33)
+    n = int(numpy.prod(shape))
+    centre = numpy.zeros(shape, bool)
+    centre[1::2, 1::2, 1::2] = True
+    src = numpy.where(centre, 1.0, 0.0).ravel()
+    snk = numpy.where(centre, 0.0, 5.0).ravel()
+    ws = []
+    for d in range(3):
+        short = list(shape); short[d] -= 1
+        ws.append(10.0 ** rng.uniform(-9, -2, size=short))
+    graph = gc.GCGraph(n, 3 * n, shape=shape)
+    graph.set_tweights_dense(src, snk)
+    for d in range(3):
+        graph.set_nweights_dense(d, ws[d], ws[d])
+    g = graph.get_graph()
+    flow = g.maxflow()
+    mask = g.get_mask()
+    assert numpy.array_equal(mask.astype(bool), centre), "a saturated centre voxel is still connected to the sink"
+    prob = et.build_problem(numpy.zeros(shape, bool), numpy.zeros(shape, bool))
+    tr = numpy.zeros(n)
+    prob["flow_const"] = et.add_tweights_pass(tr, 0.0, src, snk)
+    prob["tr"] = tr
+    prob["wf"] = prob["wb"] = et.dense_axis_arrays(shape, ws)
+    oflow, omask, _ = _oracle_solve(prob)
+    assert numpy.array_equal(mask, omask)
+    assert abs(flow - oflow) <= 1e-9 * abs(oflow)
