@@ -257,10 +257,20 @@ def roofline_from_stats(stats_list, n, peak, peak_kind):
     ]
     name, bpv, ms, cnt = max(cand, key=lambda c: c[2])
     cnt = max(cnt, 1)
+    # DRAM bytes of that kernel from the committed ncu --set full capture of this workload (profiles/), per launch
+    traffic = None
+    try:
+        if n == 512 ** 3:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_512cubed.json")))["bytes_per_launch"]
+            key = {"k_boundary": "k_boundary", "k_init_tile": "k_init_tile", "k_push_tile": "k_push_tile_tma",
+                   "k_relabel_tile": "k_bfs_coop"}[name.split(" ")[0]]
+            traffic = tj.get(key)
+    except Exception:
+        traffic = None
     avg = ms / cnt
     achieved = n * bpv / (avg * 1e-3) / 1e9 if avg > 0 else 0.0
     return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_kind": peak_kind, "launches": cnt, "avg_launch_ms": avg,
+            "traffic": traffic, "peak_kind": peak_kind, "launches": cnt, "avg_launch_ms": avg,
             "algorithmic_bytes_per_launch": n * bpv,
             "share_of_step": {c[0].split(" ")[0] + "_ms": c[2] for c in cand} | {
                 "solve_ms": sum(s["ms_solve"] for s in stats_list), "terms_ms": sum(s["ms_terms"] for s in stats_list),
