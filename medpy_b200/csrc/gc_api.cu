@@ -211,7 +211,13 @@ int alloc_buf(mgc_graph* g, size_t bytes, void** out)
 int ensure_scratch(mgc_graph* g, Buf& b, size_t bytes)
 {
     if (b.bytes >= bytes) return MGC_OK;
-    if (b.p) { pool_free(g->device, b.bytes, b.p); g->device_bytes -= (int64_t)round_up(b.bytes); }
+    if (b.p) {
+        // a kernel or copy that is still in flight may be using the old block: drain before it goes back to the pool
+        if (g->stream) cudaStreamSynchronize(g->stream);
+        if (g->up_stream) cudaStreamSynchronize(g->up_stream);
+        pool_free(g->device, b.bytes, b.p);
+        g->device_bytes -= (int64_t)round_up(b.bytes);
+    }
     b.p = nullptr; b.bytes = 0;
     void* p = nullptr;
     cudaError_t e = pool_alloc(g->device, bytes, &p);
@@ -301,6 +307,8 @@ int stage_input(mgc_graph* g, const mgc_array* a, int slot, const void** out)
         case MGC_I32: gather_launch<int32_t>(g, src, st, (int32_t*)g->scratch[slot].p); break;
     }
     CK(cudaGetLastError());
+    // the gather is the last reader of the raw span: the next upload into it (same call, e.g. bg after fg) must wait
+    if (a->mem == MGC_MEM_HOST) { CK(cudaEventRecord(g->ev_slot[3], g->stream)); g->slot_used[3] = true; }
     *out = g->scratch[slot].p;
     return MGC_OK;
 }

@@ -257,12 +257,15 @@ __device__ __forceinline__ void relabel_visit(const Lattice& L, const Tiles& TL,
     }
     if (h != h0) {
         height[c.v] = h;
-        if (c.lz == 0 && c.tz > 0) list_push(rflag, next, tile_nbr(TL, t, 0));
-        if (c.lz == TILE - 1 && c.tz + 1 < TL.nt[0]) list_push(rflag, next, tile_nbr(TL, t, 1));
-        if (c.ly == 0 && c.ty > 0) list_push(rflag, next, tile_nbr(TL, t, 2));
-        if (c.ly == TILE - 1 && c.ty + 1 < TL.nt[1]) list_push(rflag, next, tile_nbr(TL, t, 3));
-        if (c.lx == 0 && c.tx > 0) list_push(rflag, next, tile_nbr(TL, t, 4));
-        if (c.lx == TILE - 1 && c.tx + 1 < TL.nt[2]) list_push(rflag, next, tile_nbr(TL, t, 5));
+        // wake a face neighbour only if my new label can actually lower the voxel across the face: its label (from the
+        // halo, and labels only ever decrease during a BFS) must exceed mine + 1.  Without this test every tile was
+        // re-listed by each neighbour that settled after it -- most visits of a hard instance changed nothing.
+        if (c.lz == 0 && c.tz > 0 && sh[me + hoff<0>()] > h + 1) list_push(rflag, next, tile_nbr(TL, t, 0));
+        if (c.lz == TILE - 1 && c.tz + 1 < TL.nt[0] && sh[me + hoff<1>()] > h + 1) list_push(rflag, next, tile_nbr(TL, t, 1));
+        if (c.ly == 0 && c.ty > 0 && sh[me + hoff<2>()] > h + 1) list_push(rflag, next, tile_nbr(TL, t, 2));
+        if (c.ly == TILE - 1 && c.ty + 1 < TL.nt[1] && sh[me + hoff<3>()] > h + 1) list_push(rflag, next, tile_nbr(TL, t, 3));
+        if (c.lx == 0 && c.tx > 0 && sh[me + hoff<4>()] > h + 1) list_push(rflag, next, tile_nbr(TL, t, 4));
+        if (c.lx == TILE - 1 && c.tx + 1 < TL.nt[2] && sh[me + hoff<5>()] > h + 1) list_push(rflag, next, tile_nbr(TL, t, 5));
     }
 }
 

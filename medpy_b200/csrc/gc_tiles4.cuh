@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(T4_VOX) k_relabel_tile4(Lattice L, Tiles4 TL, 
             for (int k = 0; k < 8; ++k) {
                 const int ax = k >> 1;
                 const bool edge = (k & 1) ? (c.l[ax] == t4_ext(ax) - 1 && c.tc[ax] + 1 < TL.nt[ax]) : (c.l[ax] == 0 && c.tc[ax] > 0);
-                if (edge) list_push(rflag, next, tile4_nbr(TL, t, k));
+                // only if my new label can lower the voxel across the face (see relabel_visit)
+                if (edge && sh[me + ((k & 1) ? t4_hoff(ax) : -t4_hoff(ax))] > h + 1) list_push(rflag, next, tile4_nbr(TL, t, k));
             }
         }
     }
