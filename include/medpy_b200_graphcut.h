@@ -169,6 +169,14 @@ int mgc_get_node_num(const mgc_graph* g, int64_t* n);
 int mgc_get_arc_num(const mgc_graph* g, int64_t* n);
 int mgc_get_stats(const mgc_graph* g, mgc_stats* out);
 
+/* ---- pre-step of the boundary_maximum_* terms ----------------------------------- */
+
+/* bin/medpy_gradient.py:79-85: scipy.ndimage.generic_gradient_magnitude(image, prewitt, output=float32), mode 'reflect',
+ * reproduced bit for bit.  `image`: f32/f64/u8/i16/i32 array over `shape[ndim]` (1 <= ndim <= 4, any positive strides);
+ * `out`: C-contiguous float32 array of the same shape in host (MGC_MEM_HOST) or device memory. */
+int mgc_gradient_magnitude_prewitt(int32_t ndim, const int64_t* shape, const mgc_array* image, float* out,
+                                   int32_t out_mem, int32_t device);
+
 /* ---- z-slab multi-GPU stepping (driven by the host over NCCL) ------------------- */
 
 /* Number of elements of one border-plane message: the product of the extents of axes 1..ndim-1. */

@@ -9,6 +9,7 @@
 #include "gc_persist.cuh"
 #include "gc_tma.cuh"
 #include "gc_tiles4.cuh"
+#include "gc_gradient.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -946,6 +947,28 @@ int readout(mgc_graph* g, double* energy_part)
 
 }  // namespace
 
+template <typename E, int ND>
+static cudaError_t gradient_launch(const int64_t* shape, const E* img, float* out, long long n)
+{
+    GradCtx<ND> G;
+    long long st = 1;
+    for (int d = ND - 1; d >= 0; --d) { G.dim[d] = (int)shape[d]; G.stride[d] = st; st *= shape[d]; }
+    k_gradient_magnitude<E, ND><<<(unsigned)((n + 255) / 256), 256>>>(G, n, img, out);
+    return cudaGetLastError();
+}
+
+template <typename E>
+static cudaError_t gradient_dispatch(int nd, const int64_t* shape, const E* img, float* out, long long n)
+{
+    switch (nd) {
+        case 1: return gradient_launch<E, 1>(shape, img, out, n);
+        case 2: return gradient_launch<E, 2>(shape, img, out, n);
+        case 3: return gradient_launch<E, 3>(shape, img, out, n);
+        default: return gradient_launch<E, 4>(shape, img, out, n);
+    }
+}
+
+
 // =====================================================================================================
 // C ABI
 // =====================================================================================================
@@ -999,6 +1022,60 @@ int mgc_reset(mgc_graph* g)
     g->st = mgc_stats{};
     g->st.n_voxels = n;
     g->terms_open = false;
+    return MGC_OK;
+}
+
+int mgc_gradient_magnitude_prewitt(int32_t ndim, const int64_t* shape, const mgc_array* image, float* out,
+                                   int32_t out_mem, int32_t device)
+{
+    if (ndim < 1 || ndim > 4 || !shape || !image || !image->data || !out) { g_create_error = "bad arguments"; return MGC_E_ARG; }
+    const size_t es = dtype_size(image->dtype);
+    if (!es) { g_create_error = "unsupported dtype"; return MGC_E_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        g_create_error = "no usable CUDA device (this library has no CPU path)";
+        return MGC_E_CUDA;
+    }
+    if (device < 0) cudaGetDevice(&device);
+    cudaSetDevice(device);
+    long long n = 1;
+    bool contiguous = true;
+    long long expect = (long long)es;
+    for (int d = ndim - 1; d >= 0; --d) {
+        if (shape[d] < 1) { g_create_error = "extents must be >= 1"; return MGC_E_ARG; }
+        if (shape[d] > 1 && image->strides[d] != expect) contiguous = false;
+        expect *= shape[d];
+        n *= shape[d];
+    }
+    if (!contiguous) { g_create_error = "gradient input must be C-contiguous (the host layer copies otherwise)"; return MGC_E_ARG; }
+    void* d_in = nullptr;
+    void* d_out = nullptr;
+    const size_t in_bytes = (size_t)n * es, out_bytes = (size_t)n * sizeof(float);
+    cudaError_t e = cudaSuccess;
+    if (image->mem == MGC_MEM_HOST) {
+        if ((e = pool_alloc(device, in_bytes, &d_in)) != cudaSuccess) { cudaGetLastError(); g_create_error = "device allocation failed"; return MGC_E_NOMEM; }
+        e = cudaMemcpy(d_in, image->data, in_bytes, cudaMemcpyHostToDevice);
+    }
+    const void* src = image->mem == MGC_MEM_HOST ? d_in : image->data;
+    float* dst = out;
+    if (e == cudaSuccess && out_mem == MGC_MEM_HOST) {
+        if ((e = pool_alloc(device, out_bytes, &d_out)) == cudaSuccess) dst = (float*)d_out;
+    }
+    if (e == cudaSuccess) {
+        switch (image->dtype) {
+            case MGC_F32: e = gradient_dispatch<float>(ndim, shape, (const float*)src, dst, n); break;
+            case MGC_F64: e = gradient_dispatch<double>(ndim, shape, (const double*)src, dst, n); break;
+            case MGC_U8: e = gradient_dispatch<uint8_t>(ndim, shape, (const uint8_t*)src, dst, n); break;
+            case MGC_I16: e = gradient_dispatch<int16_t>(ndim, shape, (const int16_t*)src, dst, n); break;
+            default: e = gradient_dispatch<int32_t>(ndim, shape, (const int32_t*)src, dst, n); break;
+        }
+    }
+    if (e == cudaSuccess && out_mem == MGC_MEM_HOST) e = cudaMemcpy(out, d_out, out_bytes, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (d_in) pool_free(device, in_bytes, d_in);
+    if (d_out) pool_free(device, out_bytes, d_out);
+    if (e != cudaSuccess) { cudaGetLastError(); g_create_error = std::string("gradient kernel failed: ") + cudaGetErrorString(e); return MGC_E_CUDA; }
     return MGC_OK;
 }
 

@@ -249,8 +249,25 @@ private:
 
 }  // namespace
 
+py::array_t<float> gradient_magnitude_prewitt(const py::object& image, int device)
+{
+    ArrayRef r = make_ref(image, -1, "image");
+    if (r.shape.empty() || r.shape.size() > 4) throw py::value_error("image must have 1 to 4 dimensions");
+    std::vector<py::ssize_t> shp(r.shape.begin(), r.shape.end());
+    py::array_t<float> out(shp);
+    int rc;
+    {
+        float* p = out.mutable_data();
+        py::gil_scoped_release rel;
+        rc = mgc_gradient_magnitude_prewitt((int32_t)r.shape.size(), r.shape.data(), &r.a, p, MGC_MEM_HOST, device);
+    }
+    check(rc, nullptr);
+    return out;
+}
+
 PYBIND11_MODULE(_mgc, m)
 {
+    m.def("gradient_magnitude_prewitt", &gradient_magnitude_prewitt, py::arg("image"), py::arg("device") = -1);
     m.doc() = "pybind11 binding of libmedpy_b200_gc (B200 voxel graph-cut C ABI)";
     m.attr("ABI_VERSION") = mgc_abi_version();
     m.attr("SOURCE") = MGC_SOURCE;

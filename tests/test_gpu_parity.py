@@ -587,3 +587,23 @@ def test_source_clamp_leaves_no_one_ulp_residuals():
     oflow, omask, _ = _oracle_solve(prob)
     assert numpy.array_equal(mask, omask)
     assert abs(flow - oflow) <= 1e-9 * abs(oflow)
+
+
+@pytest.mark.parametrize("shape,dtype", [((9, 8, 7), numpy.float32), ((33, 20, 17), numpy.float32), ((6, 5), numpy.float64),
+                                         ((12,), numpy.float32), ((5, 4, 6, 3), numpy.float32), ((16, 9, 11), numpy.int16),
+                                         ((1, 7, 1), numpy.float32)])
+def test_gradient_magnitude_prewitt_equals_scipy(shape, dtype):
+    """bin/medpy_gradient.py:79-85 = scipy.ndimage.generic_gradient_magnitude(img, prewitt,
+    output=float32).  The arithmetic lives in SciPy (third-party dependency of the reference, present in this image);
+    the GPU kernel must reproduce it bit for bit."""
+    import scipy.ndimage as ndi
+    from medpy_b200.gradient import gradient_magnitude_prewitt
+    rng = numpy.random.default_rng(sum(shape))
+    img = (rng.normal(size=shape) * 50).astype(dtype)
+    want = numpy.zeros(shape, dtype=numpy.float32)
+    ndi.generic_gradient_magnitude(img, ndi.prewitt, output=want)
+    got = gradient_magnitude_prewitt(img)
+    assert got.dtype == numpy.float32 and got.shape == tuple(shape)
+    assert numpy.array_equal(got, want), float(numpy.abs(got - want).max())
+    # Fortran-ordered input (as medpy.io.load returns) gives the same logical result
+    assert numpy.array_equal(gradient_magnitude_prewitt(numpy.asfortranarray(img)), want)
