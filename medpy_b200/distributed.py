@@ -70,8 +70,8 @@ class SlabSolver:
         self.msg_bytes = self.h_bytes + self.plane * 8
         mk = lambda: torch.zeros(self.msg_bytes, dtype=torch.uint8, device=self.tdev)
         self.send_lo, self.send_hi, self.recv_lo, self.recv_hi = mk(), mk(), mk(), mk()
-        self.flag = torch.zeros(1, dtype=torch.int32, device=self.tdev)     # "a ghost label changed", set by unpack
-        self.count = torch.zeros(1, dtype=torch.int64, device=self.tdev)    # active voxels, written by the handle
+        # [ghost label changed in round A, ... in round B, active voxels]: written by the handle's kernels, all-reduced
+        self.stat3 = torch.zeros(3, dtype=torch.int64, device=self.tdev)
         self.passes0, self.passes_max = int(passes0), int(passes_max)
         self.stats = {"exchanges": 0, "relabel_rounds": 0, "global_relabels": 0, "push_passes": 0}
 
@@ -110,9 +110,9 @@ class SlabSolver:
     def _ptr(self, t):
         return t.data_ptr() if self.native else t
 
-    def exchange(self, want_changed=False):
+    def exchange(self, changed=None):
         """pack -> send/recv with both neighbours -> unpack; everything is enqueued on the stream, the host never
-        waits.  With ``want_changed`` the unpack kernel raises ``self.flag`` (device) if a ghost label changed."""
+        waits.  ``changed``: one-element device tensor the unpack kernel sets to 1 if a ghost label changed."""
         torch, dist = self.torch, self.dist
         hl, fl = self._views(self.send_lo)
         hh, fh = self._views(self.send_hi)
@@ -132,7 +132,7 @@ class SlabSolver:
         rhh, rfh = self._views(self.recv_hi)
         self.handle.slab_unpack(self._ptr(rhl) if self.ghost_lo else 0, self._ptr(rfl) if self.ghost_lo else 0,
                                 self._ptr(rhh) if self.ghost_hi else 0, self._ptr(rfh) if self.ghost_hi else 0,
-                                self._ptr(self.flag) if want_changed else 0)
+                                self._ptr(changed) if changed is not None else 0)
         self.stats["exchanges"] += 1
 
     def _allreduce(self, value, op):
@@ -142,36 +142,38 @@ class SlabSolver:
 
     # ---------------------------------------------------------------------------------------------- solve
     def global_relabel(self):
-        """Exact distributed backward BFS: local fixed point <-> border label exchange until nothing moves."""
+        """Exact distributed backward BFS + stop test.  Returns the global number of active voxels afterwards.
+
+        A round = local BFS to a fixed point, then a border-label exchange whose unpack raises a device flag if a ghost
+        label changed.  Almost every relabel needs exactly two rounds (one that moves labels across the borders, one that
+        confirms nothing moves any more), so two rounds and the active count are enqueued speculatively and checked with
+        ONE all-reduce + host synchronisation: [changed in round A, changed in round B, active voxels].  The count is
+        valid iff round B changed nothing anywhere; otherwise two more rounds follow."""
         dist = self.dist
         self.handle.slab_relabel_begin()
+        st = self.stat3
         while True:
-            self.handle.slab_relabel_relax(False)
-            self.flag.zero_()
-            self.exchange(want_changed=True)
-            self.stats["relabel_rounds"] += 1
+            st.zero_()
+            for k in (0, 1):
+                self.handle.slab_relabel_relax(False)
+                self.exchange(changed=st[k:k + 1])
+                self.stats["relabel_rounds"] += 1
+            self.handle.slab_count_active_dev(self._ptr(st[2:3]))
             if self.world > 1:
-                dist.all_reduce(self.flag, op=dist.ReduceOp.MAX, group=self.group)
-            if int(self.flag.item()) == 0:          # the one host synchronisation of the round
+                dist.all_reduce(st, op=dist.ReduceOp.SUM, group=self.group)
+            vals = st.tolist()                       # the one host synchronisation
+            if vals[1] == 0:
                 break
         self.stats["global_relabels"] += 1
-
-    def active(self):
-        """Global number of active voxels (device counters all-reduced; one host synchronisation)."""
-        self.handle.slab_count_active_dev(self._ptr(self.count))
-        if self.world > 1:
-            self.dist.all_reduce(self.count, op=self.dist.ReduceOp.SUM, group=self.group)
-        return int(self.count.item())
+        return int(vals[2])
 
     def solve(self, max_rounds=100000):
         """Run to a maximum preflow.  Returns this rank's energy share; use ``energy()`` for the total."""
-        dist = self.dist
         self.handle.slab_begin()
         passes = self.passes0
         rounds = 0
         while True:
-            self.global_relabel()
-            if self.active() == 0:
+            if self.global_relabel() == 0:
                 break
             rounds += 1
             if rounds > max_rounds:
