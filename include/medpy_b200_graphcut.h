@@ -113,6 +113,14 @@ int mgc_abi_version(void);
  * the block to the pool. */
 int mgc_host_alloc(size_t bytes, void** out);
 void mgc_host_free(void* p);
+/* Options.  MGC_OPT_DEFER_WEIGHT_CHECK (default 0): mgc_add_boundary on a HOST image does not wait for its kernel to
+ * report non-positive weights; the verdict (MGC_E_WEIGHT) is delivered by the next call on the handle instead (terms,
+ * markers, maxflow, mgc_check).  graph_from_voxels switches it on because it always adds the markers right after the
+ * boundary term, which lets the marker upload overlap the stencil kernel. */
+#define MGC_OPT_DEFER_WEIGHT_CHECK 1
+int mgc_set_option(mgc_graph* g, int32_t option, int64_t value);
+/* Deliver a deferred verdict now (MGC_OK / MGC_E_WEIGHT). */
+int mgc_check(mgc_graph* g);
 /* Use an externally owned cudaStream_t (e.g. torch's current stream) for all work of this handle. */
 int mgc_set_stream(mgc_graph* g, void* cuda_stream);
 int mgc_synchronize(mgc_graph* g);

@@ -131,8 +131,15 @@ struct mgc_graph {
     bool slot_used[4] = {false, false, false, false};
     cudaEvent_t ev_terms[2] = {};      // span of the term kernels since the last reset
     bool terms_open = false;
+    // deferred weight verdict (MGC_OPT_DEFER_WEIGHT_CHECK)
+    bool defer_check = false;
+    bool bad_pending = false;
+    int* h_bad = nullptr;              // pinned
+    cudaEvent_t ev_bad = nullptr;
+    cudaEvent_t ev_b[2] = {};          // the boundary kernel alone
 
     bool init_timed = false;           // ev[4..5] bracket the last k_init_tile
+    bool boundary_timed = false;       // ev[2..3]... the boundary kernel's own events (ev_b) await reading
     bool caps_fresh = true;            // capacity arrays not written yet since create/reset (hold garbage)
     bool tr_fresh = true;              // same for tr[]
     bool state_init = false;
@@ -360,8 +367,20 @@ void resolve_term_span(mgc_graph* g)
     if (cudaEventSynchronize(g->ev_terms[1]) == cudaSuccess) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, g->ev_terms[0], g->ev_terms[1]) == cudaSuccess) g->st.ms_terms += ms;
+        if (g->boundary_timed && cudaEventElapsedTime(&ms, g->ev_b[0], g->ev_b[1]) == cudaSuccess) g->st.ms_boundary = ms;
+        g->boundary_timed = false;
     }
     g->terms_open = false;
+}
+
+// deliver a deferred weight verdict: waits for the boundary kernel that produced it
+int check_pending(mgc_graph* g)
+{
+    if (!g->bad_pending) return MGC_OK;
+    g->bad_pending = false;
+    CK(cudaEventSynchronize(g->ev_bad));
+    if (*g->h_bad) FAIL(MGC_E_WEIGHT, "Negative or zero weights are not allowed.");
+    return MGC_OK;
 }
 
 // rank-3 float64 tensor maps with an 8x8x8 box over the local lattice (x fastest); driver entry point resolved at run
@@ -541,6 +560,9 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
     cudaEventCreateWithFlags(&g->ev_up, cudaEventDisableTiming);
     for (auto& ev : g->ev_slot) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto& ev : g->ev_terms) cudaEventCreate(&ev);
+    cudaEventCreateWithFlags(&g->ev_bad, cudaEventDisableTiming);
+    for (auto& ev : g->ev_b) cudaEventCreate(&ev);
+    if (cudaHostAlloc((void**)&g->h_bad, sizeof(int), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); g->h_bad = nullptr; }
     if (const char* s1 = getenv("MEDPY_GC_SWEEPS")) g->sweeps_per_round = atoi(s1) > 0 ? atoi(s1) : g->sweeps_per_round;
     if (const char* s2 = getenv("MEDPY_GC_RELAX_BATCH")) g->relax_batch = atoi(s2) > 0 ? atoi(s2) : g->relax_batch;
     g->st.n_voxels = (int64_t)n;
@@ -1001,6 +1023,9 @@ void mgc_destroy(mgc_graph* g)
     for (auto& ev : g->ev_slot) if (ev) cudaEventDestroy(ev);
     for (auto& ev : g->ev_terms) if (ev) cudaEventDestroy(ev);
     if (g->ev_up) cudaEventDestroy(g->ev_up);
+    if (g->ev_bad) cudaEventDestroy(g->ev_bad);
+    for (auto& ev : g->ev_b) if (ev) cudaEventDestroy(ev);
+    if (g->h_bad) cudaFreeHost(g->h_bad);
     if (g->up_stream) { cudaStreamSynchronize(g->up_stream); cudaStreamDestroy(g->up_stream); }
     if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
     delete g;
@@ -1022,6 +1047,7 @@ int mgc_reset(mgc_graph* g)
     g->st = mgc_stats{};
     g->st.n_voxels = n;
     g->terms_open = false;
+    g->bad_pending = false;
     return MGC_OK;
 }
 
@@ -1103,6 +1129,19 @@ void mgc_host_free(void* p)
     g_host_live.erase(it);
 }
 
+int mgc_set_option(mgc_graph* g, int32_t option, int64_t value)
+{
+    if (!g) return MGC_E_ARG;
+    if (option == MGC_OPT_DEFER_WEIGHT_CHECK) { g->defer_check = value != 0; return MGC_OK; }
+    FAIL(MGC_E_ARG, "unknown option");
+}
+
+int mgc_check(mgc_graph* g)
+{
+    if (!g) return MGC_E_ARG;
+    return check_pending(g);
+}
+
 int mgc_set_stream(mgc_graph* g, void* cuda_stream)
 {
     if (!g) return MGC_E_ARG;
@@ -1129,6 +1168,8 @@ int mgc_add_regional_probability(mgc_graph* g, const mgc_array* prob, double alp
     const void* p = nullptr;
     int rc = stage_input(g, prob, 0, &p);
     if (rc) return rc;
+    rc = check_pending(g);
+    if (rc) return rc;
     if (prob->dtype == MGC_F32)
         k_regional<float, double><<<rblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const float*)p, alpha, compute_dtype == MGC_F32, g->tr_fresh ? 1 : 0, g->partials);
     else
@@ -1154,6 +1195,8 @@ int mgc_add_tweights_dense(mgc_graph* g, const mgc_array* src, const mgc_array* 
     if (rc) return rc;
     rc = stage_input(g, snk, 1, &pk);
     if (rc) return rc;
+    rc = check_pending(g);
+    if (rc) return rc;
     k_tweights_dense<double><<<rblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const double*)ps, (const double*)pk, g->tr_fresh ? 1 : 0, g->partials);
     g->tr_fresh = false;
     g->st.kernel_launches++;
@@ -1176,6 +1219,8 @@ int mgc_add_markers(mgc_graph* g, const mgc_array* fg, const mgc_array* bg)
     int rc = MGC_OK;
     if (fg) { rc = stage_input(g, fg, 0, &pf); if (rc) return rc; }
     if (bg) { rc = stage_input(g, bg, 1, &pb); if (rc) return rc; }
+    rc = check_pending(g);      // after the uploads: they overlapped the boundary kernel whose verdict this is
+    if (rc) return rc;
     k_markers<double><<<rblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const uint8_t*)pf, (const uint8_t*)pb, g->tr_fresh ? 1 : 0, g->partials);
     g->tr_fresh = false;
     g->st.kernel_launches++;
@@ -1192,6 +1237,7 @@ int mgc_add_boundary(mgc_graph* g, int32_t kind, const mgc_array* image, double 
     if (!g || !image) return MGC_E_ARG;
     if (kind < 0 || kind > 7) FAIL(MGC_E_ARG, "unknown boundary term");
     CK(cudaSetDevice(g->device));
+    { int rc0 = check_pending(g); if (rc0) return rc0; }
     TermSpan t(g);
     const void* img = nullptr;
     int rc = stage_input(g, image, 2, &img);
@@ -1222,7 +1268,7 @@ int mgc_add_boundary(mgc_graph* g, int32_t kind, const mgc_array* image, double 
         P.norm = (kind == MGC_BOUNDARY_MAXIMUM_LINEAR) ? mm[1] : mm[0];
     }
     CK(cudaMemsetAsync(g->d_flags, 0, sizeof(int), g->stream));
-    cudaEventRecord(g->ev[2], g->stream);
+    cudaEventRecord(g->ev_b[0], g->stream);
     switch (image->dtype) {
         case MGC_F32: boundary_launch<float>(g, (const float*)img, P); break;
         case MGC_F64: boundary_launch<double>(g, (const double*)img, P); break;
@@ -1230,15 +1276,23 @@ int mgc_add_boundary(mgc_graph* g, int32_t kind, const mgc_array* image, double 
         case MGC_I16: boundary_launch<int16_t>(g, (const int16_t*)img, P); break;
         case MGC_I32: boundary_launch<int32_t>(g, (const int32_t*)img, P); break;
     }
-    cudaEventRecord(g->ev[3], g->stream);
+    cudaEventRecord(g->ev_b[1], g->stream);
     CK(cudaGetLastError());
+    invalidate(g);
+    g->has_nlinks = true;
+    g->boundary_timed = true;
+    if (g->defer_check && g->h_bad && image->mem == MGC_MEM_HOST) {
+        // verdict later: the next call's host->device copy overlaps this kernel (see MGC_OPT_DEFER_WEIGHT_CHECK)
+        CK(cudaMemcpyAsync(g->h_bad, g->d_flags, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+        CK(cudaEventRecord(g->ev_bad, g->stream));
+        g->bad_pending = true;
+        t.stop();
+        return MGC_OK;
+    }
     int bad = 0;
     CK(cudaMemcpyAsync(&bad, g->d_flags, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
     t.stop();
     CK(cudaStreamSynchronize(g->stream));      // the weight check must be reported by this call (ValueError)
-    { float ms = 0; cudaEventElapsedTime(&ms, g->ev[2], g->ev[3]); g->st.ms_boundary = ms; }
-    invalidate(g);
-    g->has_nlinks = true;
     if (bad) FAIL(MGC_E_WEIGHT, "Negative or zero weights are not allowed.");
     return MGC_OK;
 }
@@ -1249,6 +1303,7 @@ int mgc_add_nweights_dense(mgc_graph* g, int32_t axis, const mgc_array* fwd, con
     if (axis < 0 || axis >= g->user_ndim) FAIL(MGC_E_ARG, "bad axis");
     if (fwd->dtype != MGC_F64 || bwd->dtype != MGC_F64) FAIL(MGC_E_ARG, "dense n-weights must be float64");
     CK(cudaSetDevice(g->device));
+    { int rc0 = check_pending(g); if (rc0) return rc0; }
     TermSpan t(g);
     const void *pf = nullptr, *pb = nullptr;
     int rc = stage_input(g, fwd, 0, &pf);
@@ -1282,6 +1337,7 @@ int mgc_maxflow(mgc_graph* g, double* energy)
     if (g->slab) FAIL(MGC_E_STATE, "z-slab handles are stepped with mgc_slab_*");
     CK(cudaSetDevice(g->device));
     if (g->solved) { if (energy) *energy = g->energy; return MGC_OK; }
+    { int rc0 = check_pending(g); if (rc0) return rc0; }
     resolve_term_span(g);
     {
         Timer t(g, &g->st.ms_solve);
@@ -1445,6 +1501,7 @@ int mgc_slab_begin(mgc_graph* g)
 {
     if (!g) return MGC_E_ARG;
     CK(cudaSetDevice(g->device));
+    { int rc0 = check_pending(g); if (rc0) return rc0; }
     resolve_term_span(g);
     if (g->use_tiles) {
         int rc = materialise_zeros(g);

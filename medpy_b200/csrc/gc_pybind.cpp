@@ -191,6 +191,8 @@ public:
     int64_t get_node_num() { int64_t n = 0; check(mgc_get_node_num(g_, &n), g_); return n; }
     int64_t get_arc_num() { int64_t n = 0; check(mgc_get_arc_num(g_, &n), g_); return n; }
     void reset() { check(mgc_reset(g_), g_); }
+    void set_option(int option, long long value) { check(mgc_set_option(g_, option, value), g_); }
+    void check_deferred() { int rc; { py::gil_scoped_release rel; rc = mgc_check(g_); } check(rc, g_); }
     void set_stream(uintptr_t s) { check(mgc_set_stream(g_, reinterpret_cast<void*>(s)), g_); }
     void synchronize() { int rc; { py::gil_scoped_release rel; rc = mgc_synchronize(g_); } check(rc, g_); }
     py::dict stats()
@@ -272,6 +274,7 @@ PYBIND11_MODULE(_mgc, m)
     m.attr("ABI_VERSION") = mgc_abi_version();
     m.attr("SOURCE") = MGC_SOURCE;
     m.attr("SINK") = MGC_SINK;
+    m.attr("OPT_DEFER_WEIGHT_CHECK") = MGC_OPT_DEFER_WEIGHT_CHECK;
     py::class_<PyGraph>(m, "Graph")
         .def(py::init<const std::vector<int64_t>&, int>(), py::arg("shape"), py::arg("device") = -1)
         .def(py::init<const std::vector<int64_t>&, int64_t, int64_t, int>(), py::arg("shape"), py::arg("z0"), py::arg("z1"), py::arg("device") = -1)
@@ -289,6 +292,8 @@ PYBIND11_MODULE(_mgc, m)
         .def("get_node_num", &PyGraph::get_node_num)
         .def("get_arc_num", &PyGraph::get_arc_num)
         .def("reset", &PyGraph::reset)
+        .def("set_option", &PyGraph::set_option)
+        .def("check_deferred", &PyGraph::check_deferred)
         .def("set_stream", &PyGraph::set_stream)
         .def("synchronize", &PyGraph::synchronize)
         .def("stats", &PyGraph::stats)

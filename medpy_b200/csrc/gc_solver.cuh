@@ -161,7 +161,29 @@ __global__ void __launch_bounds__(256) k_readout(Lattice L, State<T> S, uint8_t*
     __shared__ double sh[8];
     double a = 0.0;
     const unsigned step = gridDim.x * blockDim.x;
-    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < L.n; v += step) {
+    // four voxels per thread and iteration (16 B label load, 32 B of sink flow, 4 B mask store); tail handled scalar
+    const unsigned n4 = L.n >> 2;
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += step) {
+        const int4 h = reinterpret_cast<const int4*>(S.height)[q];
+        uchar4 m;
+        m.x = h.x >= MGC_HINF ? 1 : 0; m.y = h.y >= MGC_HINF ? 1 : 0;
+        m.z = h.z >= MGC_HINF ? 1 : 0; m.w = h.w >= MGC_HINF ? 1 : 0;
+        reinterpret_cast<uchar4*>(mask)[q] = m;
+        const unsigned v = q << 2;
+        if (sizeof(T) == 8) {
+            const double2 s0 = reinterpret_cast<const double2*>(S.sink)[2 * q];
+            const double2 s1 = reinterpret_cast<const double2*>(S.sink)[2 * q + 1];
+            if (owned(L, v)) a = __dadd_rn(a, s0.x);
+            if (owned(L, v + 1)) a = __dadd_rn(a, s0.y);
+            if (owned(L, v + 2)) a = __dadd_rn(a, s1.x);
+            if (owned(L, v + 3)) a = __dadd_rn(a, s1.y);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (owned(L, v + i)) a = __dadd_rn(a, (double)S.sink[v + i]);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (L.n & 3u)) {
+        const unsigned v = (n4 << 2) + threadIdx.x;
         mask[v] = S.height[v] >= MGC_HINF ? 1 : 0;
         if (owned(L, v)) a = __dadd_rn(a, (double)S.sink[v]);
     }

@@ -50,6 +50,9 @@ def graph_from_voxels(fg_markers, bg_markers, regional_term=False, boundary_term
     fg_in = numpy.asarray(fg_markers)
     _logger.debug("Assuming %d nodes and %d edges for image of shape %s", fg_in.size, voxel_edge_count(fg_in.shape), fg_in.shape)
     graph = GCGraph(fg_in.size, voxel_edge_count(fg_in.shape), shape=fg_in.shape)
+    # the markers follow the boundary term immediately: a non-positive-weight ValueError may be delivered by that next
+    # call (still inside this function) so that the marker upload overlaps the stencil kernel
+    graph.get_graph().defer_weight_check(True)
 
     fg = numpy.asarray(fg_markers, dtype=numpy.bool_)
     bg = numpy.asarray(bg_markers, dtype=numpy.bool_)
@@ -76,5 +79,7 @@ def graph_from_voxels(fg_markers, bg_markers, regional_term=False, boundary_term
     # set_source_nodes(fg ids) THEN set_sink_nodes(bg ids) (generate.py:169-172) as one fused device pass.  The
     # reference skips an empty marker set; an all-False array does the same thing here, so no host-side scan.
     graph._add_markers(fg, bg)
-
-    return graph.get_graph()
+    gc_graph = graph.get_graph()
+    gc_graph.check_deferred()
+    gc_graph.defer_weight_check(False)
+    return gc_graph

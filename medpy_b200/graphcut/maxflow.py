@@ -66,6 +66,7 @@ class GraphDouble:
         self._mask = None
         self._offlattice = None
         self._pending = []
+        self._defer_weight_check = False
 
     # ------------------------------------------------------------------ native handle
     @property
@@ -76,7 +77,22 @@ class GraphDouble:
         if self._native is None:
             from .. import _lib  # raises ImportError loudly when the extension is not built
             self._native = _lib.Graph(list(self._shape), self._device)
+            if self._defer_weight_check:
+                self._native.set_option(_lib._mgc.OPT_DEFER_WEIGHT_CHECK, 1)
         return self._native
+
+    def defer_weight_check(self, on=True):
+        """Let a boundary term return before its kernel has reported non-positive weights; the ValueError is then
+        raised by the next call on the graph (graph_from_voxels adds the markers right after the boundary term, so the
+        marker upload overlaps the stencil kernel).  ``check_deferred()`` forces the verdict."""
+        self._defer_weight_check = bool(on)
+        if self._native is not None:
+            from .. import _lib
+            self._native.set_option(_lib._mgc.OPT_DEFER_WEIGHT_CHECK, 1 if on else 0)
+
+    def check_deferred(self):
+        if self._native is not None:
+            self._native.check_deferred()
 
     def _dirty(self):
         self._mask = None
