@@ -259,9 +259,12 @@ int upload(mgc_graph* g, void* dst, const void* src, size_t bytes, int slot)
 }
 
 // call after the kernel(s) that read the staging slots have been launched
-void slots_release(mgc_graph* g)
+void slots_release(mgc_graph* g, unsigned mask)
 {
-    for (int i = 0; i < 4; ++i) { cudaEventRecord(g->ev_slot[i], g->stream); g->slot_used[i] = true; }
+    // only the slots this call's kernels actually read: marking the others would make the NEXT call's upload wait for
+    // this call's kernel although it targets a different buffer
+    for (int i = 0; i < 4; ++i)
+        if (mask & (1u << i)) { cudaEventRecord(g->ev_slot[i], g->stream); g->slot_used[i] = true; }
 }
 
 int stage_input(mgc_graph* g, const mgc_array* a, int slot, const void** out)
@@ -358,7 +361,7 @@ struct TermSpan {
     {
         if (!g->terms_open) { cudaEventRecord(g->ev_terms[0], g->stream); g->terms_open = true; }
     }
-    void stop() { slots_release(g); cudaEventRecord(g->ev_terms[1], g->stream); }
+    void stop(unsigned slot_mask) { slots_release(g, slot_mask); cudaEventRecord(g->ev_terms[1], g->stream); }
 };
 
 void resolve_term_span(mgc_graph* g)
@@ -1180,7 +1183,7 @@ int mgc_add_regional_probability(mgc_graph* g, const mgc_array* prob, double alp
     rc = finish_flow_const(g);
     if (rc) return rc;
     invalidate(g);
-    t.stop();
+    t.stop(1u);
     return MGC_OK;
 }
 
@@ -1204,7 +1207,7 @@ int mgc_add_tweights_dense(mgc_graph* g, const mgc_array* src, const mgc_array* 
     rc = finish_flow_const(g);
     if (rc) return rc;
     invalidate(g);
-    t.stop();
+    t.stop(3u);
     return MGC_OK;
 }
 
@@ -1228,7 +1231,7 @@ int mgc_add_markers(mgc_graph* g, const mgc_array* fg, const mgc_array* bg)
     rc = finish_flow_const(g);
     if (rc) return rc;
     invalidate(g);
-    t.stop();
+    t.stop(3u);
     return MGC_OK;
 }
 
@@ -1286,12 +1289,12 @@ int mgc_add_boundary(mgc_graph* g, int32_t kind, const mgc_array* image, double 
         CK(cudaMemcpyAsync(g->h_bad, g->d_flags, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
         CK(cudaEventRecord(g->ev_bad, g->stream));
         g->bad_pending = true;
-        t.stop();
+        t.stop(4u);
         return MGC_OK;
     }
     int bad = 0;
     CK(cudaMemcpyAsync(&bad, g->d_flags, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
-    t.stop();
+    t.stop(4u);
     CK(cudaStreamSynchronize(g->stream));      // the weight check must be reported by this call (ValueError)
     if (bad) FAIL(MGC_E_WEIGHT, "Negative or zero weights are not allowed.");
     return MGC_OK;
@@ -1323,7 +1326,7 @@ int mgc_add_nweights_dense(mgc_graph* g, int32_t axis, const mgc_array* fwd, con
     CK(cudaGetLastError());
     int bad = 0;
     CK(cudaMemcpyAsync(&bad, g->d_flags, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
-    t.stop();
+    t.stop(3u);
     CK(cudaStreamSynchronize(g->stream));
     invalidate(g);
     g->has_nlinks = true;
