@@ -61,7 +61,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -88,8 +88,22 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         os.unlink(self.path)
+        note = "nvidia-smi -lms 20 from the start of the warm-up steps to the end of the timed steps"
+        if not sm:
+            # the whole region can be shorter than nvidia-smi's start-up: one query right after it, GPU still hot
+            try:
+                line = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                      capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0]
+                parts = [x.strip() for x in line.split(",")]
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+                note = "timed region shorter than nvidia-smi's start-up; single query immediately after it"
+            except Exception:
+                pass
         return {"sm_mhz": float(numpy.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "how": note}
 
 
 def make_volume(size):
@@ -304,11 +318,11 @@ def bench_single(vol, args, torch):
             stats.append(graph.stats())
         return e
 
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
     for _ in range(args.warmup):
         step(False)
     torch.cuda.synchronize()
-    sampler = ClockSampler(torch.cuda.current_device())
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     ev0.record(stream)

@@ -292,13 +292,13 @@ def bench_slab(shape, args, rank, world, local_rank):
         s.handle.get_mask_into(d_mask.data_ptr())
         return s.energy()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
     dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     stream = torch.cuda.current_stream()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
