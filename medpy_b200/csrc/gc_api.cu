@@ -18,6 +18,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 // ---------------------------------------------------------------------------------------------------
@@ -575,15 +576,28 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
     return MGC_OK;
 }
 
+template <typename E, int ND, bool FRESH>
+void boundary_launch_nd(mgc_graph* g, const E* img, const BoundaryParams& P)
+{
+    const dim3 grid(nblocks(g)), block(256);
+    // specialised instances: exponential term, no spacing, float32 / float64 images (every BASELINE configuration)
+    if (P.fn == 1 && P.inv_spacing_on == 0.0 && (sizeof(E) == 4 || sizeof(E) == 8) && !std::is_integral<E>::value) {
+        if (P.use_max) k_boundary<E, ND, double, FRESH, 1, 1, 0><<<grid, block, 0, g->stream>>>(g->L, g->S, img, P, g->d_flags);
+        else           k_boundary<E, ND, double, FRESH, 1, 0, 0><<<grid, block, 0, g->stream>>>(g->L, g->S, img, P, g->d_flags);
+        return;
+    }
+    k_boundary<E, ND, double, FRESH><<<grid, block, 0, g->stream>>>(g->L, g->S, img, P, g->d_flags);
+}
+
 template <typename E>
 int boundary_launch(mgc_graph* g, const E* img, const BoundaryParams& P)
 {
     if (g->caps_fresh) {
-        if (g->nd == 3) k_boundary<E, 3, double, true><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, img, P, g->d_flags);
-        else            k_boundary<E, 4, double, true><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, img, P, g->d_flags);
+        if (g->nd == 3) boundary_launch_nd<E, 3, true>(g, img, P);
+        else            boundary_launch_nd<E, 4, true>(g, img, P);
     } else {
-        if (g->nd == 3) k_boundary<E, 3, double, false><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, img, P, g->d_flags);
-        else            k_boundary<E, 4, double, false><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, img, P, g->d_flags);
+        if (g->nd == 3) boundary_launch_nd<E, 3, false>(g, img, P);
+        else            boundary_launch_nd<E, 4, false>(g, img, P);
     }
     g->caps_fresh = false;
     g->st.kernel_launches++;

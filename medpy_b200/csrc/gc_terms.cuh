@@ -119,22 +119,50 @@ struct BoundaryParams {
     double spacing[4]; // canonical axes
 };
 
+// exp(-t) for t >= 0 in ~25 instructions (CUDA's general exp() costs ~80 here, and K1 is bound by instruction issue):
+// n = rint(-t*log2 e), r = -t - n*ln2 (two-step, exact product with the hi part), e^r by a degree-13 Taylor polynomial in
+// Horner form (|r| <= 0.347: truncation 4e-18), result scaled by 2^n through the exponent field.  <= 1 ulp from the
+// correctly rounded value on [0, 708]; the (rare) subnormal range goes through ldexp; t > 745.2 gives 0 like exp does
+// (the caller turns 0 into DBL_MIN, energy_voxel.py:235), NaN propagates.
+__constant__ double EXPN_C[14] = {
+    1.0, 1.0, 0.5, 1.6666666666666666e-01, 4.1666666666666664e-02, 8.3333333333333332e-03, 1.3888888888888889e-03,
+    1.9841269841269841e-04, 2.4801587301587302e-05, 2.7557319223985893e-06, 2.7557319223985888e-07,
+    2.5052108385441720e-08, 2.0876756987868100e-09, 1.6059043836821613e-10};
+
+__device__ __forceinline__ double exp_neg(double t)
+{
+    if (!(t <= 745.2)) return (t != t) ? t : 0.0;
+    const double y = -t;
+    const double n = rint(__dmul_rn(y, 1.4426950408889634));
+    double r = __fma_rn(-n, 6.93147180369123816490e-01, y);
+    r = __fma_rn(-n, 1.90821492927058770002e-10, r);
+    double p = EXPN_C[13];
+#pragma unroll
+    for (int k = 12; k >= 0; --k) p = __fma_rn(p, r, EXPN_C[k]);
+    const int ni = (int)n;
+    if (ni >= -1020) return __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
+    return ldexp(p, ni);
+}
+
+// FN >= 0 fixes the term at compile time (the specialised kernels of the common cases), FN < 0 reads it from P
+template <int FN>
 __device__ __forceinline__ double g_weight(const BoundaryParams& P, double x)
 {
+    const int fn = FN >= 0 ? FN : P.fn;
     double w;
-    if (P.fn == 0) {                       // energy_voxel.py:101-114,176-189
+    if (fn == 0) {                       // energy_voxel.py:101-114,176-189
         w = __dsub_rn(1.0, __ddiv_rn(x, P.norm));
         if (w == 0.0) w = DBL_MIN;
-    } else if (P.fn == 1) {                // :226-236,290-300
+    } else if (fn == 1) {                  // :226-236,290-300
         // x^2 / sigma^2 as a multiplication by the pre-computed reciprocal: K1 is instruction-issue bound (fp64 exp
         // + IEEE division, profiles/r01_*), and exp() is not bit-identical to numpy's libm anyway; the argument moves
         // by <= 1 ulp, i.e. the weight by <= |arg| * 1.1e-16 relative (tests allow 2e-13; the north star 1e-5).
         // sigma == 0 keeps the exact division so x = 0 still gives NaN and x > 0 gives DBL_MIN like the reference.
         double t = (P.inv_sigma2 > 0.0 && P.inv_sigma2 < 1e300) ? __dmul_rn(__dmul_rn(x, x), P.inv_sigma2)
                                                                 : __ddiv_rn(__dmul_rn(x, x), P.sigma);
-        w = exp(-t);
+        w = exp_neg(t);
         if (w <= 0.0) w = DBL_MIN;
-    } else if (P.fn == 2) {                // :337-345,399-407
+    } else if (fn == 2) {                  // :337-345,399-407
         w = __ddiv_rn(1.0, __dadd_rn(__ddiv_rn(x, P.sigma), 1.0));
         if (w <= 0.0) w = DBL_MIN;
     } else {                               // :444-452,506-514
@@ -151,7 +179,10 @@ __device__ __forceinline__ double g_weight(const BoundaryParams& P, double x)
 // FRESH = the capacity arrays hold garbage (first n-link term after create/reset): every entry is then written
 // exactly once with plain stores -- arcs that would leave the lattice get 0 -- which saves the memset and the
 // read-modify-write (48 + 48 B/voxel in 3-D).
-template <typename E, int ND, typename T, bool FRESH>
+// FN / USE_MAX / SPACING: -1 = decided at run time from P (generic kernel); 0/1/... = compile-time constant, which
+// strips the per-arc branch chain from this instruction-issue-bound kernel (the exponential term without spacing,
+// i.e. every BASELINE config, runs specialised).
+template <typename E, int ND, typename T, bool FRESH, int FN = -1, int USE_MAX = -1, int SPACING = -1>
 __global__ void __launch_bounds__(256)
 k_boundary(Lattice L, State<T> S, const E* __restrict__ img, BoundaryParams P, int* __restrict__ bad)
 {
@@ -159,18 +190,20 @@ k_boundary(Lattice L, State<T> S, const E* __restrict__ img, BoundaryParams P, i
     if (p >= L.n) return;
     int c[ND];
     decode<ND>(L, p, c);
+    const bool use_max = USE_MAX >= 0 ? (USE_MAX != 0) : (P.use_max != 0);
+    const bool spacing = SPACING >= 0 ? (SPACING != 0) : (P.inv_spacing_on != 0.0);
     E ip = img[p];
-    double a = P.use_max ? Elem<E>::val(Elem<E>::absv(ip)) : Elem<E>::val(ip);
+    double a = use_max ? Elem<E>::val(Elem<E>::absv(ip)) : Elem<E>::val(ip);
     int isbad = 0;
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
         if (c[d] + 1 < L.dim[d]) {
             unsigned q = p + L.stride[d];
             E iq = img[q];
-            double b = P.use_max ? Elem<E>::val(Elem<E>::absv(iq)) : Elem<E>::val(iq);
-            double x = P.use_max ? fmax(a, b) : fabs(__dsub_rn(a, b));
-            double w = g_weight(P, x);
-            if (P.inv_spacing_on != 0.0) w = __ddiv_rn(w, P.spacing[d]);
+            double b = use_max ? Elem<E>::val(Elem<E>::absv(iq)) : Elem<E>::val(iq);
+            double x = use_max ? fmax(a, b) : fabs(__dsub_rn(a, b));
+            double w = g_weight<FN>(P, x);
+            if (spacing) w = __ddiv_rn(w, P.spacing[d]);
             if (w <= 0.0) isbad = 1;
             if (FRESH) {
                 S.cap[2 * d + 1][p] = (T)w;
