@@ -397,12 +397,11 @@ __device__ __forceinline__ void push_visit_staged(const Lattice& L, const Tiles&
             s_out[0 * TILE_VOX + tid] = 0; s_out[1 * TILE_VOX + tid] = 0; s_out[2 * TILE_VOX + tid] = 0;
             s_out[3 * TILE_VOX + tid] = 0; s_out[4 * TILE_VOX + tid] = 0; s_out[5 * TILE_VOX + tid] = 0;
         }
-        // bit 0: some voxel is active; bit 1: some flow moved this round.  Stop when nothing is active, or after two
-        // rounds in which flow did not move at all: excess that cannot reach the sink only climbs (it is the global
+        // Stop when nothing is active, or after two rounds in which flow did not move at all: excess that cannot reach the sink only climbs (it is the global
         // relabel that retires it), and iterating on it is wasted work
-        const int vote = __syncthreads_or(act | (moved ? 2 : 0));
-        if (!(vote & 1)) break;
-        idle_rounds = (vote & 2) ? 0 : idle_rounds + 1;
+        // (__syncthreads_or returns a truth value, not the bitwise OR: two votes)
+        if (!__syncthreads_or(act)) break;
+        idle_rounds = __syncthreads_or(moved) ? 0 : idle_rounds + 1;
         const bool stop = idle_rounds >= 2;
         // ---- pull phase: every voxel collects what its in-tile neighbours sent; labels are published ----
         if (!stop) {                                // (no flow moved in a round we stop after: nothing to pull)
