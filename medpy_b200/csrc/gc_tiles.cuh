@@ -290,7 +290,7 @@ template <int K, typename T>
 __device__ __forceinline__ void push_dir(const Lattice& L, const Tiles& TL, const State<T>& S, const TileCtx& c,
                                          const int* s_h, T* s_out, int me, int h, T& e, T& ck, int& minh,
                                          int* __restrict__ pflag, const WorkList& other_next, unsigned& nbr_listed,
-                                         unsigned& dirty, int& moved)
+                                         unsigned& dirty)
 {
     T d = 0;
     if (ck > 0) {
@@ -300,7 +300,6 @@ __device__ __forceinline__ void push_dir(const Lattice& L, const Tiles& TL, cons
             ck -= d;
             e -= d;
             dirty |= (1u << K) | 64u;
-            moved = 1;       // (do not infer this from e: a 1e-20 push leaves a 0.1 excess bit-identical)
         }
         if (ck > 0) minh = hw < minh ? hw : minh;
     }
@@ -369,10 +368,8 @@ __device__ __forceinline__ void push_visit_staged(const Lattice& L, const Tiles&
     unsigned nbr_listed = 0, dirty = 0;     // dirty: bit k = cap k changed, 64 = excess, 128 = sink flow
     __syncthreads();
 
-    int idle_rounds = 0;
     for (int it = 0; it < iters; ++it) {
         // ---- push phase: decisions from the label snapshot, own registers updated, outflow published ----
-        int moved = 0;
         const int act = (c.own && e > 0 && h < MGC_HINF) ? 1 : 0;
         int newh = h;
         if (act) {
@@ -381,35 +378,26 @@ __device__ __forceinline__ void push_visit_staged(const Lattice& L, const Tiles&
                 if (rr > 0) {
                     if (e < rr) { sf += e; e = 0; } else { e -= rr; sf = scap; }   // saturation is exact
                     dirty |= 64u | 128u;
-                    moved = 1;
                 }
             }
             int minh = MGC_HINF;
-            push_dir<0>(L, TL, S, c, s_h, s_out, me, h, e, c0, minh, pflag, other_next, nbr_listed, dirty, moved);
-            push_dir<1>(L, TL, S, c, s_h, s_out, me, h, e, c1, minh, pflag, other_next, nbr_listed, dirty, moved);
-            push_dir<2>(L, TL, S, c, s_h, s_out, me, h, e, c2, minh, pflag, other_next, nbr_listed, dirty, moved);
-            push_dir<3>(L, TL, S, c, s_h, s_out, me, h, e, c3, minh, pflag, other_next, nbr_listed, dirty, moved);
-            push_dir<4>(L, TL, S, c, s_h, s_out, me, h, e, c4, minh, pflag, other_next, nbr_listed, dirty, moved);
-            push_dir<5>(L, TL, S, c, s_h, s_out, me, h, e, c5, minh, pflag, other_next, nbr_listed, dirty, moved);
+            push_dir<0>(L, TL, S, c, s_h, s_out, me, h, e, c0, minh, pflag, other_next, nbr_listed, dirty);
+            push_dir<1>(L, TL, S, c, s_h, s_out, me, h, e, c1, minh, pflag, other_next, nbr_listed, dirty);
+            push_dir<2>(L, TL, S, c, s_h, s_out, me, h, e, c2, minh, pflag, other_next, nbr_listed, dirty);
+            push_dir<3>(L, TL, S, c, s_h, s_out, me, h, e, c3, minh, pflag, other_next, nbr_listed, dirty);
+            push_dir<4>(L, TL, S, c, s_h, s_out, me, h, e, c4, minh, pflag, other_next, nbr_listed, dirty);
+            push_dir<5>(L, TL, S, c, s_h, s_out, me, h, e, c5, minh, pflag, other_next, nbr_listed, dirty);
             // excess left => no admissible arc left => relabel above the lowest residual neighbour
             if (e > 0) newh = (minh >= MGC_HINF) ? MGC_HINF : minh + 1;
         } else {
             s_out[0 * TILE_VOX + tid] = 0; s_out[1 * TILE_VOX + tid] = 0; s_out[2 * TILE_VOX + tid] = 0;
             s_out[3 * TILE_VOX + tid] = 0; s_out[4 * TILE_VOX + tid] = 0; s_out[5 * TILE_VOX + tid] = 0;
         }
-        // Stop when nothing is active, or after two rounds in which flow did not move at all: excess that cannot reach the sink only climbs (it is the global
-        // relabel that retires it), and iterating on it is wasted work
-        // (__syncthreads_or returns a truth value, not the bitwise OR: two votes)
-        if (!__syncthreads_or(act)) break;
-        idle_rounds = __syncthreads_or(moved) ? 0 : idle_rounds + 1;
-        const bool stop = idle_rounds >= 2;
+        if (!__syncthreads_or(act)) break;       // nothing is active in this tile any more: done
         // ---- pull phase: every voxel collects what its in-tile neighbours sent; labels are published ----
-        if (!stop) {                                // (no flow moved in a round we stop after: nothing to pull)
-            pull_dir<0>(c, s_out, e, c0, dirty); pull_dir<1>(c, s_out, e, c1, dirty); pull_dir<2>(c, s_out, e, c2, dirty);
-            pull_dir<3>(c, s_out, e, c3, dirty); pull_dir<4>(c, s_out, e, c4, dirty); pull_dir<5>(c, s_out, e, c5, dirty);
-        }
+        pull_dir<0>(c, s_out, e, c0, dirty); pull_dir<1>(c, s_out, e, c1, dirty); pull_dir<2>(c, s_out, e, c2, dirty);
+        pull_dir<3>(c, s_out, e, c3, dirty); pull_dir<4>(c, s_out, e, c4, dirty); pull_dir<5>(c, s_out, e, c5, dirty);
         if (newh != h) { h = newh; s_h[me] = h; }
-        if (stop) break;
         __syncthreads();
     }
 
