@@ -170,6 +170,8 @@ struct mgc_graph {
     PushMaps maps{};                   // tensor maps of cap[0..5] and excess
     int coop_grid = 0;                 // co-resident CTAs of k_solve_coop
     int tile_iters = 8;                // synchronous push/relabel rounds per tile visit
+    int tile_iters_first = 4;          // ... in the first round after init (mostly stranded excess: measured best at 512^3)
+    int iters_now = 8;
     int passes0 = 1, passes_max = 32;  // two-colour passes per round: starts at passes0, at most doubles per round
 
     // tuning
@@ -502,7 +504,7 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
         g->n_ctas = 2 * cached_sm_count(device);   // k_push_tile is built for 2 CTAs per SM
         g->use_tiles = true;
         if (const char* sv = getenv("MEDPY_GC_SOLVER")) if (!strcmp(sv, "v0")) g->use_tiles = false;
-        if (const char* e1 = getenv("MEDPY_GC_ITERS")) if (atoi(e1) > 0) g->tile_iters = atoi(e1);
+        if (const char* e1 = getenv("MEDPY_GC_ITERS")) if (atoi(e1) > 0) g->tile_iters = g->tile_iters_first = atoi(e1);
         if (const char* e2 = getenv("MEDPY_GC_PASSES0")) if (atoi(e2) > 0) g->passes0 = atoi(e2);
         if (const char* e3 = getenv("MEDPY_GC_PASSES_MAX")) if (atoi(e3) > 0) g->passes_max = atoi(e3);
         if (const char* e4 = getenv("MEDPY_GC_COOP")) g->use_coop = atoi(e4) != 0;
@@ -841,15 +843,15 @@ int push_color(mgc_graph* g, int color)
     const int a = g->pl_sel[color], oa = g->pl_sel[1 - color];
     CK(cudaMemsetAsync(cursor(g), 0, sizeof(int), g->stream));
     if (g->nd == 4) {
-        k_push_tile4<double><<<g->n_ctas, T4_VOX, 0, g->stream>>>(g->L, g->TL4, g->S, g->smask, g->tile_iters, g->pflag, pl(g, color, a),
+        k_push_tile4<double><<<g->n_ctas, T4_VOX, 0, g->stream>>>(g->L, g->TL4, g->S, g->smask, g->iters_now, g->pflag, pl(g, color, a),
                                                                   cursor(g), pl(g, color, 1 - a), pl(g, 1 - color, oa));
     } else if (g->use_tma) {
         const size_t smem = 2 * TMA_STAGE_BYTES + 6 * TILE_VOX * sizeof(double) + 1024 * sizeof(int) + 64;
-        k_push_tile_tma<double><<<g->n_ctas, TILE_VOX, smem, g->stream>>>(g->L, g->TL, g->S, g->maps, g->tile_iters, g->pflag,
+        k_push_tile_tma<double><<<g->n_ctas, TILE_VOX, smem, g->stream>>>(g->L, g->TL, g->S, g->maps, g->iters_now, g->pflag,
                                                                           pl(g, color, a), cursor(g), pl(g, color, 1 - a),
                                                                           pl(g, 1 - color, oa));
     } else
-    k_push_tile<double><<<g->n_ctas, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S, g->tile_iters, g->pflag, pl(g, color, a),
+    k_push_tile<double><<<g->n_ctas, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S, g->iters_now, g->pflag, pl(g, color, a),
                                                                cursor(g), pl(g, color, 1 - a), pl(g, 1 - color, oa));
     CK(cudaMemsetAsync(g->d_tcount + 2 + color * 2 + a, 0, sizeof(int), g->stream));   // consumed list is empty again
     g->pl_sel[color] = 1 - a;
@@ -952,6 +954,7 @@ int solve_tiles(mgc_graph* g)
         if (active == 0) break;
         if (++rounds > g->max_rounds) FAIL(MGC_E_NOCONV, "push-relabel did not converge within the round cap");
         const double push0 = g->st.ms_push;
+        g->iters_now = rounds == 1 ? g->tile_iters_first : g->tile_iters;
         rc = push_tiles(g, passes);
         if (rc) return rc;
         // next round: at most double, and no more push time than one global relabel costs (measured, not guessed):
@@ -1533,6 +1536,7 @@ int mgc_slab_push(mgc_graph* g, int32_t n)
     if (!g || n < 0) return MGC_E_ARG;
     if (!g->state_init) FAIL(MGC_E_STATE, "call mgc_slab_begin first");
     CK(cudaSetDevice(g->device));
+    g->iters_now = g->tile_iters;
     if (g->use_tiles) return g->use_coop ? solve_coop(g, SOLVE_F_PUSH, n, nullptr) : push_tiles(g, n);
     return push_sweeps(g, n, nullptr);
 }
