@@ -1241,7 +1241,11 @@ int mgc_add_markers(mgc_graph* g, const mgc_array* fg, const mgc_array* bg)
     if (bg) { rc = stage_input(g, bg, 1, &pb); if (rc) return rc; }
     rc = check_pending(g);      // after the uploads: they overlapped the boundary kernel whose verdict this is
     if (rc) return rc;
-    k_markers<double><<<rblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const uint8_t*)pf, (const uint8_t*)pb, g->tr_fresh ? 1 : 0, g->partials);
+    const bool vec16 = !g->tr_fresh && (g->L.n % 16u) == 0u && ((uintptr_t)pf % 16u) == 0u && ((uintptr_t)pb % 16u) == 0u;
+    if (vec16)
+        k_markers16<double><<<rblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const uint4*)pf, (const uint4*)pb, g->partials);
+    else
+        k_markers<double><<<rblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const uint8_t*)pf, (const uint8_t*)pb, g->tr_fresh ? 1 : 0, g->partials);
     g->tr_fresh = false;
     g->st.kernel_launches++;
     CK(cudaGetLastError());
