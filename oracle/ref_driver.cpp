@@ -87,6 +87,31 @@ int bkref_lattice_solve(int ndim, const int64_t* shape,
     return 0;
 }
 
+// General sparse graph (region adjacency graphs of graph_from_labels, generate.py:177-338, and graphs assembled edge by
+// edge through GCGraph, graph.py:382-498).  Replays, in the given order, n_tw add_tweights calls (graph.h:415-425)
+// and m sum_edge calls (graph.h:456-480; the first call for a pair creates the arc pair, later ones accumulate), which
+// is all the reference's Python layer ever does to a graph; t-link and n-link state are independent, so the relative
+// order of the two groups does not matter.  mask_out: uint8[n], 1 unless what_segment == SINK.
+int bkref_sparse_solve(int n, int64_t m, const int32_t* ei, const int32_t* ej, const double* cap, const double* rev,
+                       int64_t n_tw, const int32_t* tw_node, const double* tw_src, const double* tw_snk,
+                       uint8_t* mask_out, double* flow_out, double* maxflow_seconds)
+{
+    if (n < 1) return -1;
+    GD* g = new GD(n, (int)(m > 0 ? m : 1), NULL);
+    g->add_node(n);
+    for (int64_t k = 0; k < n_tw; ++k) g->add_tweights(tw_node[k], tw_src[k], tw_snk[k]);
+    for (int64_t k = 0; k < m; ++k) g->sum_edge(ei[k], ej[k], cap[k], rev[k]);
+    auto t0 = std::chrono::steady_clock::now();
+    const double flow = g->maxflow();
+    auto t1 = std::chrono::steady_clock::now();
+    if (mask_out)
+        for (int v = 0; v < n; ++v) mask_out[v] = (g->what_segment(v) == GD::SINK) ? 0 : 1;
+    if (flow_out) *flow_out = flow;
+    if (maxflow_seconds) *maxflow_seconds = std::chrono::duration<double>(t1 - t0).count();
+    delete g;
+    return 0;
+}
+
 // Incremental handle API (used by tests that mirror GCGraph call by call).
 void* bkref_new(int nodes, int edges) { GD* g = new GD(nodes, edges > 0 ? edges : 1, NULL); g->add_node(nodes); return g; }
 void bkref_delete(void* h) { delete (GD*)h; }

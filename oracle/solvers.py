@@ -129,3 +129,35 @@ def solve_ref(prob, use_sum_edge=False):
     if rc != 0:
         raise RuntimeError("bkref_lattice_solve: instance exceeds the reference's int32 ids (graph.h:62,82)")
     return flow.value, mask.reshape(shape), {"fill_s": times[0], "maxflow_s": times[1], "readout_s": times[2]}
+
+
+def solve_sparse_ref(n, i, j, cap, rev, tw_ops):
+    """The real reference BK on a general sparse graph: `tw_ops` = sequence of (nodes, src, snk) array triples replayed
+    as add_tweights calls in order, then sum_edge(i[k], j[k], cap[k], rev[k]) in order (oracle/ref_driver.cpp).
+    Returns (flow, mask uint8[n] with 1 = not SINK, maxflow seconds)."""
+    lib = _load_ref()
+    c_i32_p = ctypes.POINTER(ctypes.c_int32)
+    lib.bkref_sparse_solve.restype = ctypes.c_int
+    lib.bkref_sparse_solve.argtypes = [ctypes.c_int, ctypes.c_int64, c_i32_p, c_i32_p, _c_double_p, _c_double_p,
+                                       ctypes.c_int64, c_i32_p, _c_double_p, _c_double_p, _c_u8_p, _c_double_p,
+                                       _c_double_p]
+    ei = numpy.ascontiguousarray(i, dtype=numpy.int32)
+    ej = numpy.ascontiguousarray(j, dtype=numpy.int32)
+    ec = numpy.ascontiguousarray(cap, dtype=numpy.float64)
+    er = numpy.ascontiguousarray(rev, dtype=numpy.float64)
+    if tw_ops:
+        tn = numpy.ascontiguousarray(numpy.concatenate([numpy.asarray(o[0]).ravel() for o in tw_ops]), dtype=numpy.int32)
+        ts = numpy.ascontiguousarray(numpy.concatenate([numpy.broadcast_to(numpy.asarray(o[1], dtype=numpy.float64), numpy.asarray(o[0]).shape).ravel() for o in tw_ops]))
+        tk = numpy.ascontiguousarray(numpy.concatenate([numpy.broadcast_to(numpy.asarray(o[2], dtype=numpy.float64), numpy.asarray(o[0]).shape).ravel() for o in tw_ops]))
+    else:
+        tn = numpy.zeros(0, numpy.int32)
+        ts = tk = numpy.zeros(0)
+    mask = numpy.empty(int(n), dtype=numpy.uint8)
+    flow = ctypes.c_double(0)
+    secs = ctypes.c_double(0)
+    rc = lib.bkref_sparse_solve(int(n), ei.size, ei.ctypes.data_as(c_i32_p), ej.ctypes.data_as(c_i32_p), _dptr(ec), _dptr(er),
+                                tn.size, tn.ctypes.data_as(c_i32_p), _dptr(ts), _dptr(tk),
+                                mask.ctypes.data_as(_c_u8_p), ctypes.byref(flow), ctypes.byref(secs))
+    if rc != 0:
+        raise RuntimeError("bkref_sparse_solve failed (%d)" % rc)
+    return flow.value, mask, secs.value
