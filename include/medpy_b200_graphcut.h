@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MGC_ABI_VERSION 1
+#define MGC_ABI_VERSION 2
 #define MGC_MAX_NDIM 4
 
 /* status codes */
@@ -41,6 +41,7 @@ extern "C" {
 #define MGC_E_STATE (-4)   /* call not valid in the handle's current state                      */
 #define MGC_E_WEIGHT (-5)  /* an n-link weight <= 0 was produced (GCGraph.set_nweight, graph.py:436-437) */
 #define MGC_E_NOCONV (-6)  /* solver hit its iteration cap without converging                   */
+#define MGC_E_LABELS (-7)  /* label image is not numbered 1..K (energy_label.py:444-456 raises AttributeError) */
 
 /* element types of input arrays */
 #define MGC_F32 0
@@ -214,6 +215,80 @@ int mgc_slab_count_active_dev(mgc_graph* g, unsigned long long* count_dev);
 /* Finish: build the mask of the owned planes and this slab's share of the energy
  * (flow absorbed by the owned sink links + owned add_tweights constants). */
 int mgc_slab_finish(mgc_graph* g, double* energy_part);
+
+/* ---- general sparse graphs ----------------------------------------------------- */
+
+/* The graphs of the reference that are NOT voxel lattices: the region adjacency graph graph_from_labels builds
+ * (generate.py:177-338) and graphs assembled call by call through GCGraph / GraphDouble (graph.py:382-498,
+ * wrapper.cpp:63-83; e.g. tests/graphcut_/graph.py:47).  The handle replaces GraphDouble(nodes, edges) + add_node:
+ * edges and terminal weights arrive in bulk (arrays of what would have been one call each, applied in array order with
+ * the reference's accumulation semantics), the max-flow runs on the device as a CSR push-relabel (gc_sparse.cuh). */
+typedef struct mgc_sparse mgc_sparse;
+int mgc_sparse_create(int64_t n_nodes, int32_t device, mgc_sparse** out);
+void mgc_sparse_destroy(mgc_sparse* g);
+int mgc_sparse_reset(mgc_sparse* g);                           /* Graph::reset (graph.h:133) */
+const char* mgc_sparse_last_error(const mgc_sparse* g);        /* g may be NULL: last create() failure */
+/* count x Graph::sum_edge(i[k], j[k], cap[k], rev_cap[k]) (graph.h:456-480) in order: the first call for a node pair
+ * creates its arc pair, later calls -- in either orientation -- accumulate with +=.  Host arrays.  MGC_E_ARG for ids
+ * outside [0, n) or i == j (the ValueErrors of GCGraph.set_nweight, graph.py:418-435). */
+int mgc_sparse_sum_edges(mgc_sparse* g, int64_t count, const int32_t* i, const int32_t* j, const double* cap,
+                         const double* rev_cap);
+/* count x Graph::add_tweights(nodes[k], src[k], snk[k]) (graph.h:415-425) in order; nodes == NULL means 0..count-1. */
+int mgc_sparse_add_tweights(mgc_sparse* g, int64_t count, const int32_t* nodes, const double* src, const double* snk);
+/* Graph::maxflow(): min-cut energy including the add_tweights constants.  Idempotent until the graph changes. */
+int mgc_sparse_maxflow(mgc_sparse* g, double* energy);
+/* out[v] = 0 if what_segment(v) == SINK else 1, for all n nodes (host buffer). */
+int mgc_sparse_get_mask(mgc_sparse* g, uint8_t* out);
+int mgc_sparse_what_segment(mgc_sparse* g, int64_t node, int32_t* segment);
+/* Capacity of arc i->j / net terminal capacity as assembled so far (the values the reference's getters return before
+ * maxflow(); 0 for unconnected pairs). */
+int mgc_sparse_get_edge(const mgc_sparse* g, int64_t i, int64_t j, double* cap);
+int mgc_sparse_get_trcap(const mgc_sparse* g, int64_t node, double* trcap);
+int mgc_sparse_get_node_num(const mgc_sparse* g, int64_t* n);
+int mgc_sparse_get_arc_num(const mgc_sparse* g, int64_t* n);    /* 2 per connected node pair */
+int mgc_sparse_get_stats(const mgc_sparse* g, mgc_stats* out);
+
+/* ---- label images: the region adjacency graph built on the device (row f3) ------------------------------------ */
+
+/* A label image resident in device memory.  Replaces what every energy_label term recomputes from the numpy array
+ * (energy_label.py:78-86,181-189): mgc_labels_create stages `labels` (MGC_I32, any positive strides, logical shape
+ * `shape[ndim]`, 1 <= ndim <= 4) once and runs __check_label_image (:444-456): MGC_E_LABELS unless the ids are
+ * exactly 1..K.  Region r of the image is node r-1 of the graph (generate.py:334-337). */
+typedef struct mgc_labels mgc_labels;
+int mgc_labels_create(int32_t ndim, const int64_t* shape, const mgc_array* labels, int32_t device, mgc_labels** out);
+void mgc_labels_destroy(mgc_labels* l);
+const char* mgc_labels_last_error(const mgc_labels* l);       /* l may be NULL: last create() failure */
+int mgc_labels_region_count(const mgc_labels* l, int64_t* k);
+/* Boundary terms over all border voxel pairs (2*ndim-connectivity), reduced per region pair in the reference's own
+ * accumulation order (axis by axis, C order inside an axis), so the sums equal what the chain of set_nweight ->
+ * sum_edge calls leaves in the reference's arcs:
+ *   MGC_LABELS_ADJACENCY  : __compute_edges_nd (energy_label.py:411-441): the pairs only (`values` ignored);
+ *   MGC_LABELS_STAWIASKI  : boundary_stawiaski (:123-214): w = (1/(1+max(|g_p|,|g_q|)))^2, both directions;
+ *   MGC_LABELS_STAWIASKI_DIRECTED : boundary_stawiaski_directed (:217-342) with `directedness` (incl. the double
+ *                                   count of every axis' first pair that numpy.vectorize causes there).
+ * `values` = gradient image (f32/f64/u8/i16/i32) over the same shape.  The result stays in the handle:
+ * *n_edges region pairs, fetched with mgc_labels_fetch_edges into host arrays of that length, sorted by (i, j), i < j:
+ * w_ij = capacity i->j, w_ji = capacity j->i. */
+#define MGC_LABELS_ADJACENCY 0
+#define MGC_LABELS_STAWIASKI 1
+#define MGC_LABELS_STAWIASKI_DIRECTED 2
+int mgc_labels_boundary(mgc_labels* l, int32_t kind, const mgc_array* values, double directedness, int64_t* n_edges);
+int mgc_labels_fetch_edges(const mgc_labels* l, int32_t* i, int32_t* j, double* w_ij, double* w_ji);
+/* Per-region sums of `values` and voxel counts (host arrays of K entries).
+ *   MGC_SUM_BINCOUNT : numpy.bincount(labels, weights) as used by scipy.ndimage.mean (energy_label.py:92): float64,
+ *                      front to back in C order;
+ *   MGC_SUM_PAIRWISE : numpy.sum over the region's voxels in the array's own float type (regional_atlas,
+ *                      energy_label.py:384-386): numpy's pairwise summation, reproduced exactly (integer arrays are
+ *                      summed exactly either way). */
+#define MGC_SUM_BINCOUNT 0
+#define MGC_SUM_PAIRWISE 1
+int mgc_labels_region_sums(mgc_labels* l, const mgc_array* values, int32_t mode, double* sums, int64_t* counts);
+/* flags[r] = 1 if any voxel of region r+1 is marked (numpy.unique(label_image[markers] - 1), generate.py:334-337);
+ * `markers` MGC_U8 over the same shape, flags = host array of K bytes. */
+int mgc_labels_region_flags(mgc_labels* l, const mgc_array* markers, uint8_t* flags);
+/* out[p] = per_region[label[p] - 1]: maps the cut back onto the voxels (bin/medpy_graphcut_label.py:139-148).
+ * per_region = host array of K bytes; out = C-contiguous uint8 over the shape in host or device memory. */
+int mgc_labels_apply(mgc_labels* l, const uint8_t* per_region, uint8_t* out, int32_t out_mem);
 
 #ifdef __cplusplus
 }

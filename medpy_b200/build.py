@@ -37,15 +37,42 @@ def _newer(target, sources):
     return any(os.path.getmtime(s) > t for s in sources)
 
 
+def _includes(path, seen=None):
+    """The file plus every local header it includes (transitively)."""
+    seen = seen if seen is not None else set()
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.add(path)
+    with open(path) as fh:
+        for line in fh:
+            line = line.strip()
+            if line.startswith("#include \""):
+                name = line.split('"')[1]
+                _includes(os.path.normpath(os.path.join(os.path.dirname(path), name)), seen)
+    return seen
+
+
 def build_lib(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
-    srcs.append(os.path.join(INCLUDE, "medpy_b200_graphcut.h"))
-    if not force and not _newer(LIB, srcs):
-        return LIB
-    os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-o", LIB,
-                                                                          os.path.join(CSRC, "gc_api.cu")]
-    subprocess.check_call(cmd)
+    """One object per translation unit (rebuilt only when the unit or a header it includes changed), linked into one
+    shared library: gc_api.cu (lattice path), gc_sparse_api.cu (sparse graphs + label images)."""
+    units = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    header = os.path.join(INCLUDE, "medpy_b200_graphcut.h")
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    objs = []
+    relink = force or not os.path.exists(LIB)
+    for unit in units:
+        obj = os.path.join(objdir, os.path.basename(unit)[:-3] + ".o")
+        objs.append(obj)
+        deps = sorted(_includes(unit)) + [header, os.path.abspath(__file__)]
+        if force or _newer(obj, deps):
+            cmd = [NVCC] + compile_flags + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-c", unit, "-o", obj]
+            subprocess.check_call(cmd)
+            relink = True
+    if relink or _newer(LIB, objs):
+        subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
+                               "-o", LIB] + objs)
     return LIB
 
 

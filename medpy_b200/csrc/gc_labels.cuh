@@ -157,32 +157,49 @@ __global__ void __launch_bounds__(1024) k_lab_scan_blocks(const unsigned* __rest
     for (long long b = b0; b < b1; ++b) { out[b] = acc; acc += cnt[b]; }
 }
 
-// g(max(|a|,|b|)) = (1/(1+x))^2 floored at DBL_MIN (energy_label.py:206-211,297-301).  The arithmetic type follows
-// numpy 2 promotion of `1.0 + val` / `1.0 / (...)` with val a numpy scalar of the gradient's dtype: float32 stays
-// float32 (weak Python scalars), every other dtype goes to float64; math.pow(r, 2) is then the double square.
+// g(max(|a|,|b|)) = (1/(1+x))^2 floored at DBL_MIN (energy_label.py:206-211,297-301), in the two arithmetics the
+// reference ends up using (pinned by tests/golden/golden_labels_v1.npz):
+//  * "native": numpy scalars of the gradient's dtype under numpy-2 promotion -- `1.0 + val` and `1.0 / (...)` stay
+//    float32 for a float32 gradient, every other dtype goes to float64; numpy.abs wraps at the integer minimum.
+//    Used by boundary_stawiaski and by the probing call numpy.vectorize makes on element 0.
+//  * "pyfloat": the ufunc loop of numpy.vectorize runs over dtype=object copies, i.e. Python floats / ints: float64
+//    arithmetic, abs() without wrap-around.  Used by boundary_stawiaski_directed.
+// math.pow(r, 2) is taken as the correctly rounded r*r: exact for a float32 r; for a float64 r libm's pow is within
+// one ulp of it (tests allow that ulp on float64 / integer gradients and demand equality on float32 ones).
 template <typename E> struct LabAbs;
 template <> struct LabAbs<float>   { __device__ static float  f(float x)   { return fabsf(x); } };
 template <> struct LabAbs<double>  { __device__ static double f(double x)  { return fabs(x); } };
 template <> struct LabAbs<uint8_t> { __device__ static uint8_t f(uint8_t x) { return x; } };
-template <> struct LabAbs<int16_t> { __device__ static int16_t f(int16_t x) { return (int16_t)(x < 0 ? -x : x); } };   // numpy.abs wraps at the minimum
+template <> struct LabAbs<int16_t> { __device__ static int16_t f(int16_t x) { return (int16_t)(x < 0 ? -x : x); } };
 template <> struct LabAbs<int32_t> { __device__ static int32_t f(int32_t x) { return x < 0 ? (int32_t)(0u - (unsigned)x) : x; } };
 
+template <typename E> struct LabIsF32 { static const bool v = false; };
+template <> struct LabIsF32<float> { static const bool v = true; };
+
+__device__ __forceinline__ double lab_floor_min(double w) { return (DBL_MIN > w) ? DBL_MIN : w; }   // max(w, float_info.min); NaN stays
+
 template <typename E>
-__device__ __forceinline__ double lab_stawiaski_weight(E a, E b)
+__device__ __forceinline__ double lab_weight_native(E a, E b)
 {
     const E va = LabAbs<E>::f(a), vb = LabAbs<E>::f(b);
     const E val = vb > va ? vb : va;
-    double w;
-    if (sizeof(E) == 4 && (E)0.5 != (E)0) {          // float32
+    if (LabIsF32<E>::v) {
         const float s = __fadd_rn(1.0f, (float)val);
         const float r = __fdiv_rn(1.0f, s);
-        w = __dmul_rn((double)r, (double)r);
-    } else {
-        const double s = __dadd_rn(1.0, (double)val);
-        const double r = __ddiv_rn(1.0, s);
-        w = __dmul_rn(r, r);
+        return lab_floor_min(__dmul_rn((double)r, (double)r));
     }
-    return (DBL_MIN > w) ? DBL_MIN : w;               // max(weight, sys.float_info.min); NaN stays NaN
+    const double s = __dadd_rn(1.0, (double)val);
+    const double r = __ddiv_rn(1.0, s);
+    return lab_floor_min(__dmul_rn(r, r));
+}
+
+template <typename E>
+__device__ __forceinline__ double lab_weight_pyfloat(E a, E b)
+{
+    const double va = fabs((double)a), vb = fabs((double)b);
+    const double val = vb > va ? vb : va;
+    const double r = __ddiv_rn(1.0, __dadd_rn(1.0, val));
+    return lab_floor_min(__dmul_rn(r, r));
 }
 
 // MODE 0: adjacency only (weights unused), 1: boundary_stawiaski, 2: boundary_stawiaski_directed
@@ -201,28 +218,39 @@ __global__ void __launch_bounds__(LAB_BLOCK) k_lab_pair_emit(LabGeom G, const in
     const unsigned ex = lab_block_scan(c, &total);
     if (!c) return;
     const int k1 = labels[p] - 1, k2 = labels[q] - 1;            // set_nweight(key1 - 1, key2 - 1, there, back)
-    double there = 0.0, back = 0.0;
-    if (MODE == 1) {
-        there = back = lab_stawiaski_weight<E>(grad[p], grad[q]);
-    } else if (MODE == 2) {
-        const E v1 = grad[p], v2 = grad[q];
-        const double w = lab_stawiaski_weight<E>(v1, v2);
-        const double wb = __dadd_rn(w, beta);
-        const double capped = (wb < 1.0) ? wb : 1.0;             // min(1, weight + beta)
-        const bool first_gets_beta = dark_to_light ? !(v1 > v2) : (v1 > v2);
-        there = first_gets_beta ? capped : w;
-        back = first_gets_beta ? w : capped;
-    }
     const bool fwd = k1 < k2;
     const unsigned long long lo = (unsigned long long)(fwd ? k1 : k2), hi = (unsigned long long)(fwd ? k2 : k1);
     const unsigned long long pos = block_off[blockIdx.x] + ex;
     for (unsigned r = 0; r < c; ++r) {
         keys[pos + r] = (lo << 32) | hi;
-        if (MODE != 0) {
+        if (MODE == 1) {
+            wf[pos + r] = lab_weight_native<E>(grad[p], grad[q]);
+        } else if (MODE == 2) {
+            const E v1 = grad[p], v2 = grad[q];
+            const bool probe = (c == 2u && r == 0u);             // the extra call numpy.vectorize makes on element 0
+            const double w = probe ? lab_weight_native<E>(v1, v2) : lab_weight_pyfloat<E>(v1, v2);
+            const double wb = __dadd_rn(w, beta);
+            const double capped = (wb < 1.0) ? wb : 1.0;         // min(1, weight + beta)
+            const bool first_gets_beta = dark_to_light ? !(v1 > v2) : (v1 > v2);
+            const double there = first_gets_beta ? capped : w;
+            const double back = first_gets_beta ? w : capped;
             wf[pos + r] = fwd ? there : back;
-            if (MODE == 2) wr[pos + r] = fwd ? back : there;
+            wr[pos + r] = fwd ? back : there;
         }
     }
+}
+
+__global__ void __launch_bounds__(LAB_BLOCK) k_lab_iota(unsigned* __restrict__ a, long long m)
+{
+    const long long i = (long long)blockIdx.x * LAB_BLOCK + threadIdx.x;
+    if (i < m) a[i] = (unsigned)i;
+}
+
+__global__ void __launch_bounds__(LAB_BLOCK) k_lab_permute(const double* __restrict__ src, const unsigned* __restrict__ perm, long long m,
+                                                           double* __restrict__ dst)
+{
+    const long long i = (long long)blockIdx.x * LAB_BLOCK + threadIdx.x;
+    if (i < m) dst[i] = src[perm[i]];
 }
 
 // number of distinct keys in a sorted key array
@@ -262,16 +290,17 @@ __global__ void __launch_bounds__(LAB_BLOCK) k_lab_seg_reduce(const unsigned lon
 // ---------------------------------------------------------------------------------------------------------------
 // per-region sums (numpy.bincount(labels.ravel(), weights=image.ravel()) inside scipy.ndimage.mean; regional_atlas)
 // ---------------------------------------------------------------------------------------------------------------
-template <typename E>
+template <typename E, typename V>
 __global__ void __launch_bounds__(LAB_BLOCK) k_lab_region_items(const int* __restrict__ labels, const E* __restrict__ values, long long n,
-                                                                unsigned* __restrict__ keys, double* __restrict__ vals)
+                                                                unsigned* __restrict__ keys, V* __restrict__ vals)
 {
     const long long p = (long long)blockIdx.x * LAB_BLOCK + threadIdx.x;
     if (p >= n) return;
     keys[p] = (unsigned)(labels[p] - 1);
-    vals[p] = (double)values[p];
+    vals[p] = (V)values[p];
 }
 
+// numpy.bincount(labels, weights): float64, front to back
 __global__ void __launch_bounds__(LAB_BLOCK) k_lab_region_reduce(const unsigned* __restrict__ keys, const double* __restrict__ vals, long long n,
                                                                  double* __restrict__ sums, long long* __restrict__ counts)
 {
@@ -283,6 +312,82 @@ __global__ void __launch_bounds__(LAB_BLOCK) k_lab_region_reduce(const unsigned*
     long long j = i;
     for (; j < n && keys[j] == key; ++j) a = __dadd_rn(a, vals[j]);
     sums[key] = a;
+    counts[key] = j - i;
+}
+
+// numpy.sum of a contiguous 1-D float array = numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src,
+// pairwise_sum): < 8 elements front to back; up to 128 elements eight interleaved partial sums combined as
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus a front-to-back tail; longer runs are halved (first half rounded down to
+// a multiple of 8) and the two halves added.  Checked against numpy.sum for float32/float64, n = 1..100003.
+template <typename V> __device__ __forceinline__ V lab_add(V a, V b);
+template <> __device__ __forceinline__ float lab_add<float>(float a, float b) { return __fadd_rn(a, b); }
+template <> __device__ __forceinline__ double lab_add<double>(double a, double b) { return __dadd_rn(a, b); }
+
+template <typename V>
+__device__ V lab_pairwise_leaf(const V* __restrict__ a, long long n)      // n <= 128
+{
+    if (n < 8) {
+        V res = (V)0;
+        for (long long i = 0; i < n; ++i) res = lab_add<V>(res, a[i]);
+        return res;
+    }
+    V r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    long long i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = lab_add<V>(r[j], a[i + j]);
+    }
+    V res = lab_add<V>(lab_add<V>(lab_add<V>(r[0], r[1]), lab_add<V>(r[2], r[3])),
+                       lab_add<V>(lab_add<V>(r[4], r[5]), lab_add<V>(r[6], r[7])));
+    for (; i < n; ++i) res = lab_add<V>(res, a[i]);
+    return res;
+}
+
+template <typename V>
+__device__ V lab_pairwise_sum(const V* __restrict__ a, long long n)
+{
+    if (n <= 128) return lab_pairwise_leaf<V>(a, n);
+    // explicit post-order walk of the halving tree (depth <= 40 for any n that fits memory)
+    long long fs[40], fn[40];
+    int phase[40];
+    V left[40];
+    int sp = 0;
+    fs[0] = 0; fn[0] = n; phase[0] = 0;
+    V ret = (V)0;
+    while (sp >= 0) {
+        if (fn[sp] <= 128) { ret = lab_pairwise_leaf<V>(a + fs[sp], fn[sp]); --sp; continue; }
+        long long n2 = fn[sp] / 2;
+        n2 -= n2 % 8;
+        if (phase[sp] == 0) {
+            phase[sp] = 1;
+            fs[sp + 1] = fs[sp]; fn[sp + 1] = n2; phase[sp + 1] = 0;
+            ++sp;
+        } else if (phase[sp] == 1) {
+            left[sp] = ret;
+            phase[sp] = 2;
+            fs[sp + 1] = fs[sp] + n2; fn[sp + 1] = fn[sp] - n2; phase[sp + 1] = 0;
+            ++sp;
+        } else {
+            ret = lab_add<V>(left[sp], ret);
+            --sp;
+        }
+    }
+    return ret;
+}
+
+template <typename V>
+__global__ void __launch_bounds__(LAB_BLOCK) k_lab_region_reduce_pairwise(const unsigned* __restrict__ keys, const V* __restrict__ vals, long long n,
+                                                                          double* __restrict__ sums, long long* __restrict__ counts)
+{
+    const long long i = (long long)blockIdx.x * LAB_BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const unsigned key = keys[i];
+    if (i > 0 && keys[i - 1] == key) return;
+    long long j = i;
+    while (j < n && keys[j] == key) ++j;
+    sums[key] = (double)lab_pairwise_sum<V>(vals + i, j - i);
     counts[key] = j - i;
 }
 

@@ -249,6 +249,187 @@ private:
     int64_t owned_planes_ = -1;
 };
 
+// ---- general sparse graph (mgc_sparse_*) ------------------------------------------------------------------------
+void check_sparse(int rc, const mgc_sparse* g)
+{
+    if (rc == MGC_OK) return;
+    std::string msg = mgc_sparse_last_error(g);
+    if (msg.empty()) msg = "medpy_b200 sparse graph error " + std::to_string(rc);
+    if (rc == MGC_E_ARG || rc == MGC_E_WEIGHT) throw py::value_error(msg);
+    throw std::runtime_error(msg);
+}
+
+class PySparse {
+public:
+    PySparse(int64_t n, int device)
+    {
+        int rc = mgc_sparse_create(n, device, &g_);
+        if (rc != MGC_OK) { std::string m = mgc_sparse_last_error(nullptr); if (rc == MGC_E_ARG) throw py::value_error(m); throw std::runtime_error(m); }
+    }
+    ~PySparse() { if (g_) mgc_sparse_destroy(g_); }
+    PySparse(const PySparse&) = delete;
+    PySparse& operator=(const PySparse&) = delete;
+
+    void sum_edges(py::array_t<int32_t, py::array::c_style | py::array::forcecast> i,
+                   py::array_t<int32_t, py::array::c_style | py::array::forcecast> j,
+                   py::array_t<double, py::array::c_style | py::array::forcecast> cap,
+                   py::array_t<double, py::array::c_style | py::array::forcecast> rev)
+    {
+        const py::ssize_t m = i.size();
+        if (j.size() != m || cap.size() != m || rev.size() != m) throw py::value_error("edge arrays differ in length");
+        int rc;
+        { py::gil_scoped_release rel; rc = mgc_sparse_sum_edges(g_, (int64_t)m, i.data(), j.data(), cap.data(), rev.data()); }
+        check_sparse(rc, g_);
+    }
+    void add_tweights(const py::object& nodes, py::array_t<double, py::array::c_style | py::array::forcecast> src,
+                      py::array_t<double, py::array::c_style | py::array::forcecast> snk)
+    {
+        const py::ssize_t m = src.size();
+        if (snk.size() != m) throw py::value_error("t-weight arrays differ in length");
+        py::array_t<int32_t, py::array::c_style | py::array::forcecast> nd;
+        const int32_t* np_ = nullptr;
+        if (!nodes.is_none()) {
+            nd = py::array_t<int32_t, py::array::c_style | py::array::forcecast>::ensure(nodes);
+            if (!nd || nd.size() != m) throw py::value_error("node array does not match the t-weight arrays");
+            np_ = nd.data();
+        }
+        int rc;
+        { py::gil_scoped_release rel; rc = mgc_sparse_add_tweights(g_, (int64_t)m, np_, src.data(), snk.data()); }
+        check_sparse(rc, g_);
+    }
+    double maxflow()
+    {
+        double e = 0;
+        int rc;
+        { py::gil_scoped_release rel; rc = mgc_sparse_maxflow(g_, &e); }
+        check_sparse(rc, g_);
+        return e;
+    }
+    py::array_t<uint8_t> get_mask()
+    {
+        int64_t n = 0;
+        check_sparse(mgc_sparse_get_node_num(g_, &n), g_);
+        py::array_t<uint8_t> out((py::ssize_t)n);
+        int rc;
+        { uint8_t* p = out.mutable_data(); py::gil_scoped_release rel; rc = mgc_sparse_get_mask(g_, p); }
+        check_sparse(rc, g_);
+        return out;
+    }
+    int what_segment(int64_t i) { int32_t s = 0; check_sparse(mgc_sparse_what_segment(g_, i, &s), g_); return s; }
+    double get_edge(int64_t i, int64_t j) { double c = 0; check_sparse(mgc_sparse_get_edge(g_, i, j, &c), g_); return c; }
+    double get_trcap(int64_t i) { double c = 0; check_sparse(mgc_sparse_get_trcap(g_, i, &c), g_); return c; }
+    int64_t get_node_num() { int64_t n = 0; check_sparse(mgc_sparse_get_node_num(g_, &n), g_); return n; }
+    int64_t get_arc_num() { int64_t n = 0; check_sparse(mgc_sparse_get_arc_num(g_, &n), g_); return n; }
+    void reset() { check_sparse(mgc_sparse_reset(g_), g_); }
+    py::dict stats()
+    {
+        mgc_stats s{};
+        check_sparse(mgc_sparse_get_stats(g_, &s), g_);
+        py::dict d;
+        d["n_nodes"] = s.n_voxels; d["push_sweeps"] = s.push_sweeps; d["global_relabels"] = s.global_relabels;
+        d["relabel_sweeps"] = s.relabel_sweeps; d["kernel_launches"] = s.kernel_launches; d["active_last"] = s.active_last;
+        d["ms_solve"] = s.ms_solve; d["flow_const"] = s.flow_const; d["energy"] = s.energy; d["device_bytes"] = s.device_bytes;
+        return d;
+    }
+
+private:
+    mgc_sparse* g_ = nullptr;
+};
+
+// ---- label image resident on the device (mgc_labels_*) ------------------------------------------------------------
+class PyLabels {
+public:
+    PyLabels(const py::object& labels, int device)
+    {
+        ArrayRef r = make_ref(labels, MGC_I32, "label_image");
+        if (r.shape.empty() || r.shape.size() > MGC_MAX_NDIM) throw py::value_error("label_image must have 1 to 4 dimensions");
+        shape_ = r.shape;
+        int rc;
+        { py::gil_scoped_release rel; rc = mgc_labels_create((int32_t)shape_.size(), shape_.data(), &r.a, device, &l_); }
+        if (rc != MGC_OK) {
+            std::string m = mgc_labels_last_error(nullptr);
+            if (rc == MGC_E_LABELS) { PyErr_SetString(PyExc_AttributeError, m.c_str()); throw py::error_already_set(); }
+            if (rc == MGC_E_ARG) throw py::value_error(m);
+            throw std::runtime_error(m);
+        }
+    }
+    ~PyLabels() { if (l_) mgc_labels_destroy(l_); }
+    PyLabels(const PyLabels&) = delete;
+    PyLabels& operator=(const PyLabels&) = delete;
+
+    void check(int rc) const
+    {
+        if (rc == MGC_OK) return;
+        std::string msg = mgc_labels_last_error(l_);
+        if (msg.empty()) msg = "medpy_b200 label image error " + std::to_string(rc);
+        if (rc == MGC_E_ARG) throw py::value_error(msg);
+        throw std::runtime_error(msg);
+    }
+    ArrayRef ref(const py::object& a, int want, const char* what) const
+    {
+        ArrayRef r = make_ref(a, want, what);
+        if (r.shape != shape_) throw py::value_error(std::string(what) + ": shape does not match the label image");
+        return r;
+    }
+    int64_t region_count() const { int64_t k = 0; check(mgc_labels_region_count(l_, &k)); return k; }
+
+    // -> (i, j, w_ij, w_ji), one entry per adjacent region pair, sorted by (i, j), i < j (0-based node ids)
+    py::tuple boundary(int kind, const py::object& values, double directedness)
+    {
+        ArrayRef r;
+        const bool need = kind != MGC_LABELS_ADJACENCY;
+        if (need) r = ref(values, -1, "image");
+        int64_t m = 0;
+        int rc;
+        { py::gil_scoped_release rel; rc = mgc_labels_boundary(l_, kind, need ? &r.a : nullptr, directedness, &m); }
+        check(rc);
+        py::array_t<int32_t> i((py::ssize_t)m), j((py::ssize_t)m);
+        py::array_t<double> w((py::ssize_t)m), wr((py::ssize_t)m);
+        check(mgc_labels_fetch_edges(l_, i.mutable_data(), j.mutable_data(), w.mutable_data(), wr.mutable_data()));
+        return py::make_tuple(i, j, w, wr);
+    }
+    py::tuple region_sums(const py::object& values, int mode)
+    {
+        ArrayRef r = ref(values, -1, "values");
+        const int64_t k = region_count();
+        py::array_t<double> sums((py::ssize_t)k);
+        py::array_t<int64_t> counts((py::ssize_t)k);
+        int rc;
+        {
+            double* ps = sums.mutable_data();
+            int64_t* pc = counts.mutable_data();
+            py::gil_scoped_release rel;
+            rc = mgc_labels_region_sums(l_, &r.a, mode, ps, pc);
+        }
+        check(rc);
+        return py::make_tuple(sums, counts);
+    }
+    py::array_t<uint8_t> region_flags(const py::object& markers)
+    {
+        ArrayRef r = ref(markers, MGC_U8, "markers");
+        py::array_t<uint8_t> flags((py::ssize_t)region_count());
+        int rc;
+        { uint8_t* p = flags.mutable_data(); py::gil_scoped_release rel; rc = mgc_labels_region_flags(l_, &r.a, p); }
+        check(rc);
+        return flags;
+    }
+    py::array_t<uint8_t> apply(py::array_t<uint8_t, py::array::c_style | py::array::forcecast> per_region)
+    {
+        if (per_region.size() != region_count()) throw py::value_error("one value per region expected");
+        std::vector<py::ssize_t> shp(shape_.begin(), shape_.end());
+        py::array_t<uint8_t> out(shp);
+        int rc;
+        { uint8_t* p = out.mutable_data(); const uint8_t* q = per_region.data(); py::gil_scoped_release rel; rc = mgc_labels_apply(l_, q, p, MGC_MEM_HOST); }
+        check(rc);
+        return out;
+    }
+    std::vector<int64_t> shape() const { return shape_; }
+
+private:
+    mgc_labels* l_ = nullptr;
+    std::vector<int64_t> shape_;
+};
+
 }  // namespace
 
 py::array_t<float> gradient_magnitude_prewitt(const py::object& image, int device)
@@ -275,6 +456,32 @@ PYBIND11_MODULE(_mgc, m)
     m.attr("SOURCE") = MGC_SOURCE;
     m.attr("SINK") = MGC_SINK;
     m.attr("OPT_DEFER_WEIGHT_CHECK") = MGC_OPT_DEFER_WEIGHT_CHECK;
+    m.attr("LABELS_ADJACENCY") = MGC_LABELS_ADJACENCY;
+    m.attr("LABELS_STAWIASKI") = MGC_LABELS_STAWIASKI;
+    m.attr("LABELS_STAWIASKI_DIRECTED") = MGC_LABELS_STAWIASKI_DIRECTED;
+    m.attr("SUM_BINCOUNT") = MGC_SUM_BINCOUNT;
+    m.attr("SUM_PAIRWISE") = MGC_SUM_PAIRWISE;
+    py::class_<PySparse>(m, "SparseGraph")
+        .def(py::init<int64_t, int>(), py::arg("n_nodes"), py::arg("device") = -1)
+        .def("sum_edges", &PySparse::sum_edges)
+        .def("add_tweights", &PySparse::add_tweights)
+        .def("maxflow", &PySparse::maxflow)
+        .def("get_mask", &PySparse::get_mask)
+        .def("what_segment", &PySparse::what_segment)
+        .def("get_edge", &PySparse::get_edge)
+        .def("get_trcap", &PySparse::get_trcap)
+        .def("get_node_num", &PySparse::get_node_num)
+        .def("get_arc_num", &PySparse::get_arc_num)
+        .def("reset", &PySparse::reset)
+        .def("stats", &PySparse::stats);
+    py::class_<PyLabels>(m, "LabelImage")
+        .def(py::init<const py::object&, int>(), py::arg("label_image"), py::arg("device") = -1)
+        .def("region_count", &PyLabels::region_count)
+        .def("boundary", &PyLabels::boundary, py::arg("kind"), py::arg("values") = py::none(), py::arg("directedness") = 0.0)
+        .def("region_sums", &PyLabels::region_sums)
+        .def("region_flags", &PyLabels::region_flags)
+        .def("apply", &PyLabels::apply)
+        .def_property_readonly("shape", &PyLabels::shape);
     py::class_<PyGraph>(m, "Graph")
         .def(py::init<const std::vector<int64_t>&, int>(), py::arg("shape"), py::arg("device") = -1)
         .def(py::init<const std::vector<int64_t>&, int64_t, int64_t, int>(), py::arg("shape"), py::arg("z0"), py::arg("z1"), py::arg("device") = -1)

@@ -20,10 +20,12 @@ class GCGraph:
     MAX = __UINT_16_BIT
     """The maximum value a terminal weight can take."""
 
-    def __init__(self, nodes, edges, shape=None, device=-1):
+    def __init__(self, nodes, edges, shape=None, device=-1, sparse=None):
         """``GCGraph(nodes, edges)`` as in the reference (graph.py:294-308); ``shape`` (given by
-        ``graph_from_voxels``) is the logical lattice shape whose C-order flat index is the node id."""
-        self.__graph = GraphDouble(int(nodes), int(edges), shape=shape, device=device)
+        ``graph_from_voxels``) is the logical lattice shape whose C-order flat index is the node id.  Without a shape
+        the graph is general: it moves to the sparse backend with the first edge between arbitrary nodes, or at once
+        with ``sparse=True`` (``graph_from_labels``)."""
+        self.__graph = GraphDouble(int(nodes), int(edges), shape=shape, device=device, sparse=sparse)
         self.__graph.add_node(int(nodes))
         self.__nodes = int(nodes)
         self.__edges = int(edges)
@@ -91,6 +93,34 @@ class GCGraph:
         elif weight_there <= 0 or weight_back <= 0:
             raise ValueError("Negative or zero weights are not allowed.")
         self.__graph.sum_edge(int(node_from), int(node_to), float(weight_there), float(weight_back))
+
+    def set_nweights_bulk(self, nodes_from, nodes_to, weights_there, weights_back):
+        """Array form of ``set_nweight``: one call per entry, in order, with the same checks (graph.py:418-437)."""
+        i = numpy.asarray(nodes_from).ravel()
+        j = numpy.asarray(nodes_to).ravel()
+        wt = numpy.asarray(weights_there, dtype=numpy.float64).ravel()
+        wb = numpy.asarray(weights_back, dtype=numpy.float64).ravel()
+        if not (i.size == j.size == wt.size == wb.size):
+            raise ValueError("edge arrays differ in length")
+        if i.size == 0:
+            return
+        if i.max() >= self.__nodes or i.min() < 0:
+            raise ValueError("Invalid node id (node_from) of {} or {}. Valid values are 0 to {}.".format(i.max(), i.min(), self.__nodes - 1))
+        if j.max() >= self.__nodes or j.min() < 0:
+            raise ValueError("Invalid node id (node_to) of {} or {}. Valid values are 0 to {}.".format(j.max(), j.min(), self.__nodes - 1))
+        if (i == j).any():
+            raise ValueError("The node_from can not be equal to the node_to (self-connections are forbidden in graph cuts).")
+        if (wt <= 0).any() or (wb <= 0).any():
+            raise ValueError("Negative or zero weights are not allowed.")
+        self.__graph.sum_edges_bulk(i, j, wt, wb)
+
+    def set_tweights_bulk(self, nodes, weights_source, weights_sink):
+        """Array form of ``set_tweight`` (graph.py:462-498): one add_tweights call per entry, in order."""
+        nodes = numpy.asarray(nodes).ravel()
+        if nodes.size and (nodes.max() >= self.__nodes or nodes.min() < 0):
+            raise ValueError("Invalid node id of {} or {}. Valid values are 0 to {}.".format(nodes.max(), nodes.min(), self.__nodes - 1))
+        self.__graph.add_tweights_bulk(nodes, numpy.asarray(weights_source, dtype=numpy.float64),
+                                       numpy.asarray(weights_sink, dtype=numpy.float64))
 
     def set_nweights(self, nweights):
         """graph.py:442-460."""

@@ -41,7 +41,12 @@ class GraphDouble:
 
     termtype = _termtype
 
-    def __init__(self, node_num_max, edge_num_max=0, shape=None, device=-1):
+    def __init__(self, node_num_max, edge_num_max=0, shape=None, device=-1, sparse=None):
+        # Without a lattice shape the graph starts as a 1-D chain (what element-wise users of the voxel path build) and
+        # keeps a journal of its calls; the first edge that does not join chain neighbours -- or sparse=True -- moves
+        # it, journal and all, onto the general sparse backend (sparse.py).
+        self._sp = None
+        self._journal = [] if shape is None else None
         if shape is None:
             shape = (int(node_num_max),)
         shape = tuple(int(s) for s in shape)
@@ -67,6 +72,33 @@ class GraphDouble:
         self._offlattice = None
         self._pending = []
         self._defer_weight_check = False
+        if sparse:
+            if self._journal is None:
+                raise ValueError("a lattice shape and sparse=True exclude each other")
+            self._to_sparse()
+
+    def _to_sparse(self):
+        from .sparse import SparseGraphDouble
+        sp = SparseGraphDouble(self._n, self._edges, device=self._device)
+        for op in self._journal or []:
+            if op[0] == "e":
+                sp.sum_edge(op[1], op[2], op[3], op[4])
+            elif op[0] == "t":
+                sp.add_tweights(op[1], op[2], op[3])
+            else:
+                sp.add_tweights_bulk(op[1], op[2], op[3])
+        self._journal = None
+        self._sp = sp
+        # drop the chain-lattice staging and device state
+        self._st_src = self._st_snk = self._st_touched = None
+        self._st_nw = {}
+        self._pending = []
+        self._native = None
+        self._mask = None
+
+    @property
+    def is_sparse(self):
+        return self._sp is not None
 
     # ------------------------------------------------------------------ native handle
     @property
@@ -74,6 +106,9 @@ class GraphDouble:
         return self._shape
 
     def _nat(self):
+        if self._sp is not None:
+            raise TypeError("this graph is a general sparse graph: lattice terms (energy_voxel.*) need a graph created "
+                            "with a lattice shape")
         if self._native is None:
             from .. import _lib  # raises ImportError loudly when the extension is not built
             self._native = _lib.Graph(list(self._shape), self._device)
@@ -114,6 +149,10 @@ class GraphDouble:
     def stage_tweights_many(self, ids, cap_source, cap_sink):
         """add_tweights(v, cap_source, cap_sink) for every v in ids, in order (ids already range-checked)."""
         ids = numpy.asarray(ids, dtype=numpy.int64)
+        if self._sp is not None:
+            return self._sp.stage_tweights_many(ids, cap_source, cap_sink)
+        if self._journal is not None:
+            self._journal.append(("T", ids.copy(), numpy.full(ids.size, float(cap_source)), numpy.full(ids.size, float(cap_sink))))
         self._dirty()
         self._open_tweight_batch()
         if numpy.unique(ids).size == ids.size:
@@ -125,7 +164,7 @@ class GraphDouble:
             self._st_touched[ids] = True
         else:
             for v in ids:
-                self.add_tweights(int(v), cap_source, cap_sink)
+                self._add_tweights_staged(int(v), cap_source, cap_sink)
 
     def _flush(self):
         self._close_tweight_batch()
@@ -190,6 +229,13 @@ class GraphDouble:
         i = int(i)
         if i < 0 or i >= self._n:
             raise ValueError("Invalid node id of {}. Valid values are 0 to {}.".format(i, self._n - 1))
+        if self._sp is not None:
+            return self._sp.add_tweights(i, cap_source, cap_sink)
+        if self._journal is not None:
+            self._journal.append(("t", i, float(cap_source), float(cap_sink)))
+        self._add_tweights_staged(i, cap_source, cap_sink)
+
+    def _add_tweights_staged(self, i, cap_source, cap_sink):
         self._open_tweight_batch()
         if self._st_touched[i]:
             self._close_tweight_batch()  # add_tweights is order dependent per node: start a new batch
@@ -213,12 +259,20 @@ class GraphDouble:
         i, j = int(i), int(j)
         if i < 0 or j < 0 or i >= self._n or j >= self._n or i == j:
             raise ValueError("invalid node ids ({}, {})".format(i, j))
+        if self._sp is not None:
+            return self._sp.sum_edge(i, j, cap, rev_cap)
         axis = self._axis_of(i, j)
         if axis is None:
-            # accepted like the reference would, but it can never be solved here: general sparse graphs are
-            # outside the voxel path; maxflow() refuses.
+            if self._journal is not None:
+                # not a chain neighbour: this is a general graph (tests/graphcut_/graph.py:47) -> sparse backend
+                self._to_sparse()
+                return self._sp.sum_edge(i, j, cap, rev_cap)
+            # a lattice graph (graph_from_voxels) accepts the call like the reference would, but an edge between
+            # non-neighbours can never be solved on the lattice; maxflow() refuses.
             self._offlattice = (i, j)
             return
+        if self._journal is not None:
+            self._journal.append(("e", i, j, float(cap), float(rev_cap)))
         if axis not in self._st_nw:
             self._st_nw[axis] = [numpy.zeros(self._n, dtype=numpy.float64), numpy.zeros(self._n, dtype=numpy.float64)]
         fwd, bwd = self._st_nw[axis]
@@ -232,18 +286,38 @@ class GraphDouble:
 
     add_edge = sum_edge  # graph.h:427-454: parallel arcs act as summed capacities
 
+    def sum_edges_bulk(self, i, j, cap, rev_cap):
+        """One sum_edge call per array entry, in order (general graphs: moves the graph to the sparse backend)."""
+        if self._sp is None:
+            if self._journal is None:
+                raise ValueError("bulk edges between arbitrary nodes need a graph without lattice shape")
+            self._to_sparse()
+        self._sp.sum_edges_bulk(i, j, cap, rev_cap)
+
+    def add_tweights_bulk(self, nodes, src, snk):
+        """One add_tweights call per array entry, in order."""
+        if self._sp is not None:
+            return self._sp.add_tweights_bulk(nodes, src, snk)
+        nodes = numpy.arange(len(src)) if nodes is None else numpy.asarray(nodes)
+        for v, a, b in zip(nodes.tolist(), numpy.asarray(src, dtype=float).tolist(), numpy.asarray(snk, dtype=float).tolist()):
+            self.add_tweights(v, a, b)
+
     def maxflow(self):
         """Graph::maxflow (maxflow.cpp:471-604): min-cut energy including the add_tweights constants."""
+        if self._sp is not None:
+            return self._sp.maxflow()
         if self._offlattice is not None:
             raise NotImplementedError(
-                "edge {} does not join lattice neighbours of shape {}: general sparse graphs are outside the "
-                "voxel path (SURVEY.md §8 row f4)".format(self._offlattice, self._shape))
+                "edge {} does not join lattice neighbours of shape {}: build general graphs with "
+                "GraphDouble(nodes, edges) (no shape), which uses the sparse backend".format(self._offlattice, self._shape))
         self._flush()
         return self._nat().maxflow()
 
     def get_mask(self):
         """Bulk read-out: uint8 array of the lattice shape, 0 where what_segment == SINK else 1
         (what bin/medpy_graphcut_voxel.py:177-181 builds voxel by voxel)."""
+        if self._sp is not None:
+            return self._sp.get_mask()
         if self._mask is None:
             self.maxflow()
             self._mask = self._nat().get_mask()
@@ -251,6 +325,8 @@ class GraphDouble:
 
     def what_segment(self, i, default_segm=None):
         """graph.h:560-571."""
+        if self._sp is not None:
+            return self._sp.what_segment(i)
         m = self.get_mask()
         i = int(i)
         if i < 0 or i >= self._n:
@@ -258,6 +334,10 @@ class GraphDouble:
         return _termtype.SOURCE if m.flat[i] else _termtype.SINK
 
     def reset(self):
+        if self._sp is not None:
+            return self._sp.reset()
+        if self._journal is not None:
+            self._journal = []
         self._st_src = self._st_snk = self._st_touched = None
         self._st_nw = {}
         self._mask = None
@@ -267,10 +347,14 @@ class GraphDouble:
             self._native.reset()
 
     def get_edge(self, i, j):
+        if self._sp is not None:
+            return self._sp.get_edge(i, j)
         self._flush()
         return self._nat().get_edge(int(i), int(j))
 
     def get_trcap(self, i):
+        if self._sp is not None:
+            return self._sp.get_trcap(i)
         self._flush()
         return self._nat().get_trcap(int(i))
 
@@ -278,10 +362,14 @@ class GraphDouble:
         return self._n
 
     def get_arc_num(self):
+        if self._sp is not None:
+            return self._sp.get_arc_num()
         self._flush()
         return self._nat().get_arc_num()
 
     def stats(self):
+        if self._sp is not None:
+            return self._sp.stats()
         return self._nat().stats()
 
 

@@ -25,13 +25,13 @@ def test_cabi_exports_every_declared_symbol():
     missing = [name for name in declared if not hasattr(lib, name)]
     assert not missing, missing
     lib.mgc_abi_version.restype = ctypes.c_int
-    assert lib.mgc_abi_version() == 1
+    assert lib.mgc_abi_version() == 2
 
 
 def test_pybind_module_imports_and_matches_abi():
     _ensure_built()
     from medpy_b200 import _lib
-    assert _lib.ABI_VERSION == 1 and _lib.SOURCE == 0 and _lib.SINK == 1
+    assert _lib.ABI_VERSION == 2 and _lib.SOURCE == 0 and _lib.SINK == 1
 
 
 def test_no_cpu_fallback_without_device():
@@ -84,9 +84,18 @@ def test_gcgraph_error_conventions():
     assert graph.get_node_count() == nodes
     assert graph.get_edge_count() == edges
     assert graph.get_nodes() == list(range(nodes))
-    # a non-lattice edge was accepted above; solving such a graph is outside the voxel path
+    # a non-chain edge was accepted above: the graph moved to the general sparse backend,
+    # which -- like everything else -- has no CPU solver
+    assert graph.get_graph().is_sparse
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            graph.get_graph().maxflow()
+    # a graph with a lattice shape still refuses edges between non-neighbours
+    lattice = GCGraph(6, 7, shape=(2, 3))
+    lattice.set_nweight(0, 5, 1, 1)
     with pytest.raises(NotImplementedError):
-        graph.get_graph().maxflow()
+        lattice.get_graph().maxflow()
 
 
 def test_term_callables_keep_reference_signature():
