@@ -17,6 +17,8 @@
 
 #include <cuda_runtime.h>
 
+#include "gc_pairwise.cuh"
+
 #define LAB_BLOCK 256
 
 struct LabGeom {
@@ -313,68 +315,6 @@ __global__ void __launch_bounds__(LAB_BLOCK) k_lab_region_reduce(const unsigned*
     for (; j < n && keys[j] == key; ++j) a = __dadd_rn(a, vals[j]);
     sums[key] = a;
     counts[key] = j - i;
-}
-
-// numpy.sum of a contiguous 1-D float array = numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src,
-// pairwise_sum): < 8 elements front to back; up to 128 elements eight interleaved partial sums combined as
-// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus a front-to-back tail; longer runs are halved (first half rounded down to
-// a multiple of 8) and the two halves added.  Checked against numpy.sum for float32/float64, n = 1..100003.
-template <typename V> __device__ __forceinline__ V lab_add(V a, V b);
-template <> __device__ __forceinline__ float lab_add<float>(float a, float b) { return __fadd_rn(a, b); }
-template <> __device__ __forceinline__ double lab_add<double>(double a, double b) { return __dadd_rn(a, b); }
-
-template <typename V>
-__device__ V lab_pairwise_leaf(const V* __restrict__ a, long long n)      // n <= 128
-{
-    if (n < 8) {
-        V res = (V)0;
-        for (long long i = 0; i < n; ++i) res = lab_add<V>(res, a[i]);
-        return res;
-    }
-    V r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = a[j];
-    long long i = 8;
-    for (; i < n - (n % 8); i += 8) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = lab_add<V>(r[j], a[i + j]);
-    }
-    V res = lab_add<V>(lab_add<V>(lab_add<V>(r[0], r[1]), lab_add<V>(r[2], r[3])),
-                       lab_add<V>(lab_add<V>(r[4], r[5]), lab_add<V>(r[6], r[7])));
-    for (; i < n; ++i) res = lab_add<V>(res, a[i]);
-    return res;
-}
-
-template <typename V>
-__device__ V lab_pairwise_sum(const V* __restrict__ a, long long n)
-{
-    if (n <= 128) return lab_pairwise_leaf<V>(a, n);
-    // explicit post-order walk of the halving tree (depth <= 40 for any n that fits memory)
-    long long fs[40], fn[40];
-    int phase[40];
-    V left[40];
-    int sp = 0;
-    fs[0] = 0; fn[0] = n; phase[0] = 0;
-    V ret = (V)0;
-    while (sp >= 0) {
-        if (fn[sp] <= 128) { ret = lab_pairwise_leaf<V>(a + fs[sp], fn[sp]); --sp; continue; }
-        long long n2 = fn[sp] / 2;
-        n2 -= n2 % 8;
-        if (phase[sp] == 0) {
-            phase[sp] = 1;
-            fs[sp + 1] = fs[sp]; fn[sp + 1] = n2; phase[sp + 1] = 0;
-            ++sp;
-        } else if (phase[sp] == 1) {
-            left[sp] = ret;
-            phase[sp] = 2;
-            fs[sp + 1] = fs[sp] + n2; fn[sp + 1] = fn[sp] - n2; phase[sp + 1] = 0;
-            ++sp;
-        } else {
-            ret = lab_add<V>(left[sp], ret);
-            --sp;
-        }
-    }
-    return ret;
 }
 
 template <typename V>

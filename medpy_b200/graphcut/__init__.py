@@ -1,15 +1,16 @@
-"""``medpy_b200.graphcut`` -- B200-native drop-in for the voxel half of ``medpy.graphcut``.
+"""``medpy_b200.graphcut`` -- B200-native drop-in for ``medpy.graphcut``'s graph construction and min-cut.
 
-Exports the names the reference package exports for this path (medpy/graphcut/__init__.py:186-222):
-``graph_from_voxels``, the ``energy_voxel`` module, ``GCGraph``, ``split_marker`` and the ``maxflow`` module
-with ``GraphDouble`` / ``GraphFloat`` / ``GraphInt``.  The label/region path (``graph_from_labels``,
-``energy_label``, ``graphcut_split`` ...) is outside this path's scope.
+Exports the names the reference package exports (medpy/graphcut/__init__.py:186-222): ``graph_from_voxels`` and the
+``energy_voxel`` module (the voxel path), ``graph_from_labels`` and the ``energy_label`` module (the
+region path, §8 row f3), ``GCGraph``, ``split_marker`` and the ``maxflow`` module with ``GraphDouble`` /
+``GraphFloat`` / ``GraphInt`` (general sparse graphs: row f4).  Not provided: ``graphcut_split`` / ``graphcut_stawiaski``
+/ ``graphcut_subprocesses`` (multiprocessing wrappers around the above, wrapper.py:72-329) and ``graph_to_dimacs``.
 """
-from . import energy_voxel, maxflow
-from .generate import graph_from_voxels
+from . import energy_label, energy_voxel, maxflow
+from .generate import graph_from_labels, graph_from_voxels, label_cut_mask
 from .graph import GCGraph
 from .maxflow import GraphDouble, GraphFloat, GraphInt
 from .wrapper import split_marker
 
-__all__ = ["graph_from_voxels", "energy_voxel", "GCGraph", "GraphDouble", "GraphFloat", "GraphInt",
-           "split_marker", "maxflow"]
+__all__ = ["graph_from_voxels", "graph_from_labels", "label_cut_mask", "energy_voxel", "energy_label", "GCGraph",
+           "GraphDouble", "GraphFloat", "GraphInt", "split_marker", "maxflow"]

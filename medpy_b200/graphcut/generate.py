@@ -1,5 +1,5 @@
-"""Host-side mirror of ``medpy.graphcut.generate.graph_from_voxels`` (reference:
-medpy/graphcut/generate.py:33-174).
+"""Host-side mirror of ``medpy.graphcut.generate`` (reference: medpy/graphcut/generate.py): ``graph_from_voxels``
+(:33-174) and ``graph_from_labels`` (:177-338).
 
 Same signature, same validation and the same order of operations -- regional term, boundary term, foreground
 markers, background markers (generate.py:159-172) -- but no edge list is built: the GCGraph handed to the
@@ -83,3 +83,74 @@ def graph_from_voxels(fg_markers, bg_markers, regional_term=False, boundary_term
     gc_graph.check_deferred()
     gc_graph.defer_weight_check(False)
     return gc_graph
+
+
+def _noop_label_term(graph, label_image, term_args):
+    """Default for a missing term of graph_from_labels (generate.py:346-360)."""
+    return {}
+
+
+def _takes_three_parameters(fn):
+    return hasattr(fn, "__call__") and 3 == len(inspect.getfullargspec(fn)[0])
+
+
+def graph_from_labels(label_image, fg_markers, bg_markers, regional_term=False, boundary_term=False,
+                      regional_term_args=False, boundary_term_args=False):
+    """Create a graph-cut ready graph from a label (region) image -- generate.py:177-338.
+
+    Every region of ``label_image`` (ids exactly 1..K, ``AttributeError`` otherwise) is a node (id = label - 1);
+    ``regional_term`` / ``boundary_term`` are callables ``(graph, label_image, term_args)`` (see ``energy_label``;
+    ``AttributeError`` for any other arity) that add t- and n-weights; regions touched by a foreground / background
+    marker are then tied to the source / sink with ``GCGraph.MAX`` (set_source_nodes before set_sink_nodes,
+    generate.py:334-337).  Returns the solver-side graph object offering ``maxflow()``, ``what_segment(i)``,
+    ``get_mask()`` and ``termtype``.
+
+    The label image is staged on the device once and shared by the terms and the marker step; the resulting region
+    graph is solved by the sparse push-relabel (csrc/gc_sparse.cuh).  (The reference itself cannot run this function on
+    Python >= 3.11: it calls ``inspect.getargspec``, generate.py:280.)
+    """
+    from .energy_label import LabelContext
+    label_image = numpy.asarray(label_image)
+    fg = numpy.asarray(fg_markers, dtype=numpy.bool_)
+    bg = numpy.asarray(bg_markers, dtype=numpy.bool_)
+    if not regional_term:
+        regional_term = _noop_label_term
+    if not boundary_term:
+        boundary_term = _noop_label_term
+    # (both this and a malformed label image are AttributeErrors in the reference, generate.py:272-289)
+    if not _takes_three_parameters(regional_term):
+        raise AttributeError("regional_term has to be a callable object which takes three parameters.")
+    if not _takes_three_parameters(boundary_term):
+        raise AttributeError("boundary_term has to be a callable object which takes three parameters.")
+    context = LabelContext(label_image)                      # stages the image; __check_label_image (generate.py:272)
+
+    nodes = context.regions
+    edges = 10 * nodes                                       # the reference's guess (generate.py:296)
+    _logger.debug("guessed: #nodes=%d nodes / #edges=%d", nodes, edges)
+    graph = GCGraph(nodes, edges, sparse=True)
+    graph._label_context = context
+
+    _logger.info("Computing and adding terminal edge weights...")
+    regional_term(graph, label_image, regional_term_args)
+    _logger.info("Computing and adding inter-node edge weights...")
+    boundary_term(graph, label_image, boundary_term_args)
+
+    _logger.info("Setting terminal weights for the markers...")
+    # numpy.unique(label_image[markers] - 1) (generate.py:334-337): one flag per region, set on the device
+    graph.set_source_nodes(numpy.nonzero(context.region_flags(fg))[0])
+    graph.set_sink_nodes(numpy.nonzero(context.region_flags(bg))[0])
+    gc_graph = graph.get_graph()
+    gc_graph.label_context = context                         # lets callers map the cut back: see label_cut_mask
+    return gc_graph
+
+
+def label_cut_mask(gc_graph, label_image=None):
+    """Voxel mask of a region cut: 1 where the voxel's region is not in the SINK set -- the mapping + relabel_map step
+    of bin/medpy_graphcut_label.py:139-148 as one device gather.  ``gc_graph`` is what ``graph_from_labels`` returned."""
+    from .energy_label import LabelContext
+    context = getattr(gc_graph, "label_context", None)
+    if label_image is not None and (context is None or context.source is not label_image):
+        context = LabelContext(label_image)
+    if context is None:
+        raise ValueError("pass the label image the graph was built from")
+    return context.apply(gc_graph.get_mask())

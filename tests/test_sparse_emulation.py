@@ -122,3 +122,21 @@ def test_golden_region_graphs(emu):
             e, got = run_emu(emu, n, i, j, cap, rev, tw)
             assert numpy.array_equal(got, G[nm + "/" + tag + "_mask"]), (nm, tag)
             assert e == pytest.approx(float(G[nm + "/" + tag + "_flow"]), rel=1e-9, abs=1e-300), (nm, tag)
+
+
+def test_pairwise_sum_equals_numpy_sum(tmp_path):
+    """csrc/gc_pairwise.cuh (what the regional_atlas reduction runs per region) against numpy.sum, bit for bit."""
+    so = str(tmp_path / "libpairwise_emu.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", "-o", so,
+                           os.path.join(HERE, "emu", "pairwise_emu.cpp")])
+    lib = ctypes.CDLL(so)
+    lib.emu_pairwise_f32.restype = ctypes.c_float
+    lib.emu_pairwise_f32.argtypes = [ctypes.c_void_p, ctypes.c_longlong]
+    lib.emu_pairwise_f64.restype = ctypes.c_double
+    lib.emu_pairwise_f64.argtypes = [ctypes.c_void_p, ctypes.c_longlong]
+    rng = numpy.random.default_rng(7)
+    for n in list(range(1, 300)) + [1000, 1001, 4097, 65536, 100003]:
+        a32 = rng.uniform(0, 1, n).astype(numpy.float32)
+        a64 = rng.normal(0, 100, n)
+        assert numpy.float32(lib.emu_pairwise_f32(a32.ctypes.data, n)) == numpy.sum(a32), n
+        assert lib.emu_pairwise_f64(a64.ctypes.data, n) == numpy.sum(a64), n
