@@ -8,7 +8,9 @@
 // adjacency graph there (gc_labels.cuh); only per-region / per-region-pair results ever reach the host.
 // The stable radix sort that orders the contributions by key is cub::DeviceRadixSort (CUDA toolkit).
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -76,6 +78,7 @@ struct mgc_sparse {
     int sweeps_per_round = 16;                         // push launches between two global relabels
     int relax_batch = 8;                               // relaxation launches per "changed" read-back
     int64_t max_rounds = 1000000;
+    double max_seconds = 600.0;                        // wall-clock cap of one solve (MEDPY_GC_SPARSE_TIMEOUT overrides)
     mgc_stats st{};
     std::string err;
 };
@@ -156,6 +159,7 @@ int sparse_solve(mgc_sparse* g)
     g->st.kernel_launches++;
     int64_t rounds = 0;
     long long active = 0;
+    const auto t_start = std::chrono::steady_clock::now();
     for (;;) {
         // exact global relabel: backward BFS from the sink by in-place relaxation
         k_sp_relabel_init<<<blocks, 256>>>(S);
@@ -178,9 +182,11 @@ int sparse_solve(mgc_sparse* g)
         SPCK(cudaMemcpy(&c, d_count, sizeof(c), cudaMemcpyDeviceToHost));
         active = (long long)c;
         if (!active) break;
-        if (++rounds > g->max_rounds) {
+        const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+        if (++rounds > g->max_rounds || elapsed > g->max_seconds) {
             cudaEventDestroy(ev0); cudaEventDestroy(ev1);
-            SPFAIL(MGC_E_NOCONV, "sparse push-relabel did not converge");
+            SPFAIL(MGC_E_NOCONV, "sparse push-relabel did not converge within " + std::to_string(rounds) + " rounds / " +
+                                     std::to_string(elapsed) + " s (" + std::to_string(active) + " active nodes left)");
         }
         for (int s = 0; s < g->sweeps_per_round; ++s) k_sp_push<<<blocks, 256>>>(S, g->push_steps, d_flags + 1);
         g->st.kernel_launches += g->sweeps_per_round;
@@ -230,6 +236,8 @@ int mgc_sparse_create(int64_t n_nodes, int32_t device, mgc_sparse** out)
     g->device = device;
     g->n = n_nodes;
     g->tr.assign((size_t)n_nodes, 0.0);
+    if (const char* e = std::getenv("MEDPY_GC_SPARSE_TIMEOUT")) { const double v = std::atof(e); if (v > 0) g->max_seconds = v; }
+    if (const char* e = std::getenv("MEDPY_GC_SPARSE_SWEEPS")) { const int v = std::atoi(e); if (v > 0) g->sweeps_per_round = v; }
     *out = g;
     return MGC_OK;
 }

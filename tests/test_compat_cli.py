@@ -87,3 +87,70 @@ def test_own_cli_matches_oracle(tmp_path):
     prob = et.build_problem(vol["fg"], vol["bg"], boundary=("difference_exponential", vol["image"], 15.0, (2.0, 1.0, 1.0)))
     oflow, omask, _ = solvers.solve_port(prob)
     assert numpy.array_equal(mask_xyz.T.astype(numpy.uint8), omask)
+
+
+REF_LABEL_CLI = "/root/reference/bin/medpy_graphcut_label.py"
+
+
+def _write_label_case(tmp_path, shape=(12, 10, 9)):
+    sys.path.insert(0, COMPAT)
+    try:
+        from medpy.io import save, Header
+    finally:
+        sys.path.remove(COMPAT)
+    from medpy_b200 import synthetic
+    vol = synthetic.two_blob_volume(shape, seed=5, with_prob=False)
+    grids = numpy.meshgrid(*[numpy.arange(s) for s in shape], indexing="ij")
+    regions = sum((g // 3) * m for g, m in zip(grids, (100, 10, 1))) + 7          # arbitrary ids: the CLI relabels
+    grad = numpy.sqrt(sum(d ** 2 for d in numpy.gradient(vol["image"].astype(numpy.float64)))).astype(numpy.float32)
+    markers = (vol["fg"].astype(numpy.uint8) + 2 * vol["bg"].astype(numpy.uint8))
+    hdr = Header(spacing=(1.0, 1.0, 1.0), offset=(0.0, 0.0, 0.0))
+    paths = {}
+    for name, arr in (("grad", grad), ("regions", regions.astype(numpy.int32)), ("markers", markers)):
+        paths[name] = str(tmp_path / (name + ".mha"))
+        save(numpy.ascontiguousarray(arr).T, paths[name], hdr, True)
+    return vol, regions, grad, paths
+
+
+@pytest.mark.skipif(not os.path.exists(REF_LABEL_CLI), reason="reference tree not present")
+def test_reference_label_cli_runs_unchanged_up_to_the_device(tmp_path):
+    """bin/medpy_graphcut_label.py in place and unmodified: medpy.filter.relabel, medpy.graphcut.graph_from_labels,
+    energy_label.boundary_stawiaski, what_segment per region and medpy.filter.relabel_map all come from the shim."""
+    import torch
+    vol, regions, grad, paths = _write_label_case(tmp_path)
+    out = str(tmp_path / "out.mha")
+    env = dict(os.environ, PYTHONPATH=COMPAT + os.pathsep + ROOT, PYTHONDONTWRITEBYTECODE="1")
+    r = subprocess.run([sys.executable, REF_LABEL_CLI, paths["grad"], paths["regions"], paths["markers"], out, "-f"],
+                       env=env, capture_output=True, text=True, timeout=300)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert os.path.exists(out)
+    else:
+        assert r.returncode != 0
+        assert "no CPU" in r.stderr or "CUDA" in r.stderr, r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_own_label_cli_matches_oracle(tmp_path):
+    from oracle import energy_label_terms as elt, solvers
+    vol, regions, grad, paths = _write_label_case(tmp_path, shape=(18, 15, 12))
+    out = str(tmp_path / "out.mha")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "medpy_b200", "cli", "graphcut_label.py"), paths["grad"],
+                        paths["regions"], paths["markers"], out, "-f"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    sys.path.insert(0, COMPAT)
+    try:
+        from medpy.io import load
+        from medpy.filter import relabel
+        mask_xyz, _ = load(out)
+        lab_xyz = relabel(numpy.ascontiguousarray(regions.astype(numpy.int32)).T)     # what the CLI cut: x,y,z order
+    finally:
+        sys.path.remove(COMPAT)
+    if not solvers.have_ref():
+        pytest.skip("oracle/_ref not built")
+    g_xyz, fg_xyz, bg_xyz = grad.T, vol["fg"].T, vol["bg"].T
+    i, j, w, wr = elt.stawiaski_calls(lab_xyz, g_xyz)
+    fgr, bgr = elt.marker_regions(lab_xyz, fg_xyz), elt.marker_regions(lab_xyz, bg_xyz)
+    tw = [(fgr, numpy.full(fgr.size, 65535.0), numpy.zeros(fgr.size)), (bgr, numpy.zeros(bgr.size), numpy.full(bgr.size, 65535.0))]
+    _, rmask, _ = solvers.solve_sparse_ref(int(lab_xyz.max()), i, j, w, wr, tw)
+    assert numpy.array_equal(numpy.asarray(mask_xyz).astype(numpy.uint8), rmask[lab_xyz - 1])

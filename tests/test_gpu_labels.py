@@ -23,6 +23,7 @@ from oracle import energy_label_terms as elt  # noqa: E402
 from oracle import solvers  # noqa: E402
 
 pytestmark = pytest.mark.gpu
+os.environ.setdefault("MEDPY_GC_SPARSE_TIMEOUT", "30")    # test graphs are tiny: fail fast instead of spinning
 
 G = numpy.load(os.path.join(HERE, "golden", "golden_labels_v1.npz"))
 NAMES = [str(n) for n in G["names"]]
