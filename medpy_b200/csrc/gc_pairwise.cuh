@@ -56,10 +56,10 @@ template <typename V>
 PW_HD V lab_pairwise_sum(const V* a, long long n)
 {
     if (n <= 128) return lab_pairwise_leaf<V>(a, n);
-    // explicit post-order walk of the halving tree (depth < 40 for any n that fits memory)
-    long long fs[40], fn[40];
-    int phase[40];
-    V left[40];
+    // explicit post-order walk of the halving tree (depth <= 25 for n < 2^31)
+    long long fs[32], fn[32];
+    int phase[32];
+    V left[32];
     int sp = 0;
     fs[0] = 0; fn[0] = n; phase[0] = 0;
     V ret = (V)0;

@@ -27,7 +27,7 @@ def supervoxels(n, cell, seed):
     nb = -(-n // cell)
     for axis in range(3):
         idx = numpy.arange(n).reshape([-1 if a == axis else 1 for a in range(3)])
-        jit = numpy.clip(idx + rng.integers(-1, 2, size=shape), 0, n - 1) // cell
+        jit = numpy.clip(idx + rng.integers(-1, 2, size=shape) * (rng.random(shape) < 0.15), 0, n - 1) // cell
         lab = lab * nb + jit
     _, inv = numpy.unique(lab, return_inverse=True)
     return (inv + 1).reshape(shape).astype(numpy.int32)
