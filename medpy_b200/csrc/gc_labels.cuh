@@ -255,38 +255,40 @@ __global__ void __launch_bounds__(LAB_BLOCK) k_lab_permute(const double* __restr
     if (i < m) dst[i] = src[perm[i]];
 }
 
-// number of distinct keys in a sorted key array
-__global__ void __launch_bounds__(LAB_BLOCK) k_lab_seg_count(const unsigned long long* __restrict__ keys, long long m,
-                                                             unsigned long long* __restrict__ count)
+// runs of equal keys in the sorted key array: heads per block (-> exclusive scan -> output slot of every run, so the
+// region pairs come out ordered by key without any further sort)
+__global__ void __launch_bounds__(LAB_BLOCK) k_lab_seg_head_count(const unsigned long long* __restrict__ keys, long long m,
+                                                                  unsigned* __restrict__ block_count)
 {
     const long long i = (long long)blockIdx.x * LAB_BLOCK + threadIdx.x;
-    const bool head = i < m && (i == 0 || keys[i - 1] != keys[i]);
-    const unsigned b = __ballot_sync(0xffffffffu, head);
-    if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, (unsigned long long)__popc(b));
+    const unsigned head = (i < m && (i == 0 || keys[i - 1] != keys[i])) ? 1u : 0u;
+    unsigned total;
+    lab_block_scan(head, &total);
+    if (threadIdx.x == 0) block_count[blockIdx.x] = total;
 }
 
 // one thread per run of equal keys: front-to-back float64 sum (the order `r_cap += w` sees in the reference)
 __global__ void __launch_bounds__(LAB_BLOCK) k_lab_seg_reduce(const unsigned long long* __restrict__ keys, const double* __restrict__ wf,
                                                               const double* __restrict__ wr, long long m,
-                                                              unsigned long long* __restrict__ cursor, long long capacity,
+                                                              const unsigned long long* __restrict__ block_off,
                                                               unsigned long long* __restrict__ out_key, double* __restrict__ out_f,
                                                               double* __restrict__ out_r)
 {
     const long long i = (long long)blockIdx.x * LAB_BLOCK + threadIdx.x;
-    if (i >= m) return;
+    const unsigned head = (i < m && (i == 0 || keys[i - 1] != keys[i])) ? 1u : 0u;
+    unsigned total;
+    const unsigned ex = lab_block_scan(head, &total);
+    if (!head) return;
     const unsigned long long key = keys[i];
-    if (i > 0 && keys[i - 1] == key) return;
     double a = 0.0, b = 0.0;
     for (long long j = i; j < m && keys[j] == key; ++j) {
         if (wf) a = __dadd_rn(a, wf[j]);
         if (wr) b = __dadd_rn(b, wr[j]);
     }
-    const unsigned long long pos = atomicAdd(cursor, 1ull);
-    if ((long long)pos < capacity) {
-        out_key[pos] = key;
-        out_f[pos] = a;
-        out_r[pos] = wr ? b : a;
-    }
+    const unsigned long long pos = block_off[blockIdx.x] + ex;
+    out_key[pos] = key;
+    out_f[pos] = a;
+    out_r[pos] = wr ? b : a;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

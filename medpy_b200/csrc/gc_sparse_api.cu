@@ -68,7 +68,8 @@ struct mgc_sparse {
     int64_t n = 0;
     std::vector<double> tr;                            // net terminal capacity per node
     double flow_const = 0.0;                           // sum of the add_tweights minima (graph.h:423)
-    std::unordered_map<uint64_t, int64_t> pair_of;     // (lo << 32 | hi) -> index into the pair arrays
+    std::unordered_map<uint64_t, int64_t> pair_of;     // (lo << 32 | hi) -> index into the pair arrays (built on demand)
+    bool indexed = true;                               // pair_of covers every pair
     std::vector<int32_t> plo, phi;                     // node pairs in insertion order, lo < hi
     std::vector<double> cap_lh, cap_hl;                // capacity lo->hi, hi->lo
     bool solved = false;
@@ -100,6 +101,16 @@ struct mgc_sparse {
     } while (0)
 
 namespace {
+
+void sparse_ensure_index(mgc_sparse* g)
+{
+    if (g->indexed) return;
+    g->pair_of.clear();
+    g->pair_of.reserve(g->plo.size() * 2);
+    for (size_t p = 0; p < g->plo.size(); ++p)
+        g->pair_of.emplace(((uint64_t)(uint32_t)g->plo[p] << 32) | (uint32_t)g->phi[p], (int64_t)p);
+    g->indexed = true;
+}
 
 int sparse_solve(mgc_sparse* g)
 {
@@ -250,6 +261,7 @@ int mgc_sparse_reset(mgc_sparse* g)
     std::fill(g->tr.begin(), g->tr.end(), 0.0);
     g->flow_const = 0.0;
     g->pair_of.clear();
+    g->indexed = true;
     g->plo.clear(); g->phi.clear(); g->cap_lh.clear(); g->cap_hl.clear();
     g->solved = false;
     g->energy = 0.0;
@@ -271,6 +283,28 @@ int mgc_sparse_sum_edges(mgc_sparse* g, int64_t count, const int32_t* i, const i
                                   std::to_string(g->n - 1) + ".");
         if (a == b) SPFAIL(MGC_E_ARG, "The node_from (" + std::to_string(a) + ") can not be equal to the node_to (" + std::to_string(b) + ") (self-connections are forbidden in graph-cuts).");
     }
+    // A batch of distinct pairs in strictly increasing (i, j) order with i < j -- what the region adjacency reduction
+    // delivers (mgc_labels_fetch_edges) -- landing in an empty graph needs no look-ups: append, index later if ever needed.
+    if (g->plo.empty() && count > 0) {
+        bool sorted_unique = true;
+        uint64_t prev = 0;
+        for (int64_t k = 0; k < count && sorted_unique; ++k) {
+            const uint64_t key = ((uint64_t)(uint32_t)i[k] << 32) | (uint32_t)j[k];
+            sorted_unique = i[k] < j[k] && (k == 0 || key > prev);
+            prev = key;
+        }
+        if (sorted_unique) {
+            g->plo.assign(i, i + count);
+            g->phi.assign(j, j + count);
+            g->cap_lh.assign(cap, cap + count);
+            g->cap_hl.assign(rev_cap, rev_cap + count);
+            g->pair_of.clear();
+            g->indexed = false;
+            g->solved = false;
+            return MGC_OK;
+        }
+    }
+    sparse_ensure_index(g);
     for (int64_t k = 0; k < count; ++k) {
         const bool fwd = i[k] < j[k];
         const int32_t lo = fwd ? i[k] : j[k], hi = fwd ? j[k] : i[k];
@@ -342,6 +376,7 @@ int mgc_sparse_what_segment(mgc_sparse* g, int64_t node, int32_t* segment)
 int mgc_sparse_get_edge(const mgc_sparse* g, int64_t i, int64_t j, double* cap)
 {
     if (!g || !cap) return MGC_E_ARG;
+    sparse_ensure_index(const_cast<mgc_sparse*>(g));   // the index is a cache: building it does not change the graph
     *cap = 0.0;
     if (i < 0 || j < 0 || i >= g->n || j >= g->n || i == j) return MGC_OK;
     const bool fwd = i < j;
@@ -499,36 +534,32 @@ int lab_boundary_run(mgc_labels* l, const E* grad, double directedness)
         LBCK(cub::DeviceRadixSort::SortKeys(tmp, tb, keys, keys_sorted, m, 0, end_bit, 0));
     }
     LBCK(cudaGetLastError());
-    unsigned long long* counter;
-    LBCK(dev.alloc(&counter, 2));
-    LBCK(cudaMemset(counter, 0, 2 * sizeof(unsigned long long)));
-    k_lab_seg_count<<<mblocks, LAB_BLOCK>>>(keys_sorted, m, counter);
+    // one output slot per run of equal keys, in key order (heads per block -> scan -> slot)
+    unsigned* head_count;
+    unsigned long long* head_off;
+    LBCK(dev.alloc(&head_count, (size_t)mblocks));
+    LBCK(dev.alloc(&head_off, (size_t)mblocks + 1));
+    k_lab_seg_head_count<<<mblocks, LAB_BLOCK>>>(keys_sorted, m, head_count);
+    k_lab_scan_blocks<<<1, 1024>>>(head_count, (long long)mblocks, head_off);
     unsigned long long u = 0;
-    LBCK(cudaMemcpy(&u, counter, sizeof(u), cudaMemcpyDeviceToHost));
+    LBCK(cudaMemcpy(&u, head_off + mblocks, sizeof(u), cudaMemcpyDeviceToHost));
     unsigned long long* out_key;
     double *out_f, *out_r;
     LBCK(dev.alloc(&out_key, (size_t)u));
     LBCK(dev.alloc(&out_f, (size_t)u));
     LBCK(dev.alloc(&out_r, (size_t)u));
-    k_lab_seg_reduce<<<mblocks, LAB_BLOCK>>>(keys_sorted, wf_s, wr_s, m, counter + 1, (long long)u, out_key, out_f, out_r);
-    l->kernel_launches += 2;
+    k_lab_seg_reduce<<<mblocks, LAB_BLOCK>>>(keys_sorted, wf_s, wr_s, m, head_off, out_key, out_f, out_r);
+    l->kernel_launches += 3;
     LBCK(cudaGetLastError());
     std::vector<unsigned long long> hk((size_t)u);
-    std::vector<double> hf((size_t)u), hr((size_t)u);
+    l->ew.resize((size_t)u); l->er.resize((size_t)u);
     LBCK(cudaMemcpy(hk.data(), out_key, (size_t)u * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    LBCK(cudaMemcpy(hf.data(), out_f, (size_t)u * sizeof(double), cudaMemcpyDeviceToHost));
-    LBCK(cudaMemcpy(hr.data(), out_r, (size_t)u * sizeof(double), cudaMemcpyDeviceToHost));
-    // the runs were appended in whatever order their threads finished: order the (few) region pairs by key
-    std::vector<size_t> ord((size_t)u);
-    std::iota(ord.begin(), ord.end(), (size_t)0);
-    std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return hk[a] < hk[b]; });
-    l->ei.resize((size_t)u); l->ej.resize((size_t)u); l->ew.resize((size_t)u); l->er.resize((size_t)u);
+    LBCK(cudaMemcpy(l->ew.data(), out_f, (size_t)u * sizeof(double), cudaMemcpyDeviceToHost));
+    LBCK(cudaMemcpy(l->er.data(), out_r, (size_t)u * sizeof(double), cudaMemcpyDeviceToHost));
+    l->ei.resize((size_t)u); l->ej.resize((size_t)u);
     for (size_t t = 0; t < (size_t)u; ++t) {
-        const size_t s = ord[t];
-        l->ei[t] = (int32_t)(hk[s] >> 32);
-        l->ej[t] = (int32_t)(hk[s] & 0xffffffffull);
-        l->ew[t] = hf[s];
-        l->er[t] = hr[s];
+        l->ei[t] = (int32_t)(hk[t] >> 32);
+        l->ej[t] = (int32_t)(hk[t] & 0xffffffffull);
     }
     return MGC_OK;
 }

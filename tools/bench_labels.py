@@ -45,12 +45,12 @@ def volume(n, cell, seed):
     return supervoxels(n, cell, seed), grad.astype(numpy.float32), vol["fg"], vol["bg"]
 
 
-def gpu_run(n, cell):
+def gpu_run(n, cell, reps=3):
     import medpy_b200.graphcut as gc
     lab, grad, fg, bg = volume(n, cell, 1)
     t = {}
     best = None
-    for rep in range(3):
+    for rep in range(reps):
         t0 = time.perf_counter()
         g = gc.graph_from_labels(lab, fg, bg, boundary_term=gc.energy_label.boundary_stawiaski, boundary_term_args=grad)
         t1 = time.perf_counter()
@@ -90,11 +90,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sizes", default="128,256")
     ap.add_argument("--cell", type=int, default=4)
-    ap.add_argument("--cpu-size", type=int, default=64)
+    ap.add_argument("--cpu-size", type=int, default=64, help="0 skips the CPU arm")
+    ap.add_argument("--reps", type=int, default=3)
     args = ap.parse_args()
-    print(json.dumps(dict(arm="cpu_oracle", **cpu_run(args.cpu_size, args.cell))), flush=True)
+    if args.cpu_size > 0:
+        print(json.dumps(dict(arm="cpu_oracle", **cpu_run(args.cpu_size, args.cell))), flush=True)
     for n in [int(s) for s in args.sizes.split(",") if s]:
-        print(json.dumps(dict(arm="gpu", **gpu_run(n, args.cell))), flush=True)
+        print(json.dumps(dict(arm="gpu", **gpu_run(n, args.cell, args.reps))), flush=True)
 
 
 if __name__ == "__main__":
