@@ -1190,7 +1190,9 @@ int mgc_add_regional_probability(mgc_graph* g, const mgc_array* prob, double alp
     if (rc) return rc;
     rc = check_pending(g);
     if (rc) return rc;
-    if (prob->dtype == MGC_F32)
+    if (prob->dtype == MGC_F32 && (g->L.n % 4u) == 0u && ((uintptr_t)p % 16u) == 0u)
+        k_regional_f32x4<double><<<rblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const float4*)p, alpha, compute_dtype == MGC_F32, g->tr_fresh ? 1 : 0, g->partials);
+    else if (prob->dtype == MGC_F32)
         k_regional<float, double><<<rblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const float*)p, alpha, compute_dtype == MGC_F32, g->tr_fresh ? 1 : 0, g->partials);
     else
         k_regional<double, double><<<rblocks(g), 256, 0, g->stream>>>(g->L, g->S, (const double*)p, alpha, 0, g->tr_fresh ? 1 : 0, g->partials);

@@ -297,6 +297,48 @@ k_regional(Lattice L, State<T> S, const E* __restrict__ prob, double alpha, int 
     block_sum_store(m, partials);
 }
 
+// float32 probability map, four voxels per thread: one 16-byte load of the map and two 16-byte stores of tr per
+// iteration keep enough bytes in flight to run the pass at HBM rate (the scalar form above has one 4-byte load per
+// thread outstanding and stops at 4.3 TB/s).  Requires n % 4 == 0 and a 16-byte aligned map; same arithmetic.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_regional_f32x4(Lattice L, State<T> S, const float4* __restrict__ prob, double alpha, int compute_f32, int fresh,
+                 double* __restrict__ partials)
+{
+    double m = 0.0;
+    const unsigned groups = L.n >> 2;
+    const unsigned step = gridDim.x * blockDim.x;
+    const float af = (float)alpha;
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < groups; q += step) {
+        const float4 p4 = __ldg(prob + q);
+        const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+        double2 t01 = make_double2(0.0, 0.0), t23 = make_double2(0.0, 0.0);
+        if (!fresh) {
+            t01 = reinterpret_cast<const double2*>(S.tr)[2 * q];
+            t23 = reinterpret_cast<const double2*>(S.tr)[2 * q + 1];
+        }
+        double trv[4] = {t01.x, t01.y, t23.x, t23.y};
+        const unsigned v = q << 2;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double s, t;
+            if (compute_f32) {
+                s = (double)__fmul_rn(pv[k], af);
+                t = (double)__fmul_rn(__fsub_rn(1.0f, pv[k]), af);
+            } else {
+                const double p = (double)pv[k];
+                s = __dmul_rn(p, alpha);
+                t = __dmul_rn(__dsub_rn(1.0, p), alpha);
+            }
+            const double mm = add_tweights_dev(trv[k], s, t);
+            if (owned(L, v + k)) m = __dadd_rn(m, mm);
+        }
+        reinterpret_cast<double2*>(S.tr)[2 * q] = make_double2(trv[0], trv[1]);
+        reinterpret_cast<double2*>(S.tr)[2 * q + 1] = make_double2(trv[2], trv[3]);
+    }
+    block_sum_store(m, partials);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_tweights_dense(Lattice L, State<T> S, const double* __restrict__ src, const double* __restrict__ snk,
