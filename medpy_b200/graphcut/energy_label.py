@@ -131,10 +131,10 @@ def boundary_stawiaski(graph, label_image, gradient_image):
     _add_edges(graph, i, j, w, w_back)
 
 
-def boundary_stawiaski_directed(graph, label_image, xxx_todo_changeme):
+def boundary_stawiaski_directed(graph, label_image, term_args):
     """energy_label.py:217-342: as ``boundary_stawiaski`` with ``min(1, g + |directedness|)`` on the direction the
     sign of ``directedness`` favours."""
-    (gradient_image, directedness) = xxx_todo_changeme
+    (gradient_image, directedness) = term_args
     ctx = _context(graph, label_image)
     values = ctx.values(gradient_image, "gradient_image")
     _refuse_size_one_axes(ctx.shape)
@@ -142,9 +142,9 @@ def boundary_stawiaski_directed(graph, label_image, xxx_todo_changeme):
     _add_edges(graph, i, j, w, w_back)
 
 
-def regional_atlas(graph, label_image, xxx_todo_changeme1):
+def regional_atlas(graph, label_image, term_args):
     """energy_label.py:345-396: set_tweight(region, alpha * S, -alpha * S), S = sum of the atlas under the region."""
-    (probability_map, alpha) = xxx_todo_changeme1
+    (probability_map, alpha) = term_args
     ctx = _context(graph, label_image)
     prob = numpy.asarray(probability_map)
     sums, _ = ctx.native.region_sums(ctx.values(prob, "probability_map"), ctx._mgc.SUM_PAIRWISE)
