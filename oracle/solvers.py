@@ -131,14 +131,36 @@ def solve_ref(prob, use_sum_edge=False):
     return flow.value, mask.reshape(shape), {"fill_s": times[0], "maxflow_s": times[1], "readout_s": times[2]}
 
 
+_SPARSE_PORT_SO = os.path.join(_HERE, "_build", "libbk_sparse.so")
+_sparse_port = None
+
+
+def solve_sparse_port(n, i, j, cap, rev, tw_ops):
+    """BK restatement for general graphs (oracle/bk_sparse.c); same contract as solve_sparse_ref."""
+    global _sparse_port
+    if _sparse_port is None:
+        if not os.path.exists(_SPARSE_PORT_SO) or os.path.getmtime(_SPARSE_PORT_SO) < os.path.getmtime(os.path.join(_HERE, "bk_sparse.c")):
+            subprocess.check_call(["make", "-s", "-C", _HERE, "port"])
+        _sparse_port = ctypes.CDLL(_SPARSE_PORT_SO)
+    return _solve_sparse(_sparse_port.bk_sparse_solve, n, i, j, cap, rev, tw_ops)
+
+
+def solve_sparse(n, i, j, cap, rev, tw_ops):
+    """The real reference solver where it is built, otherwise the restatement (they agree bit for bit)."""
+    return (solve_sparse_ref if have_ref() else solve_sparse_port)(n, i, j, cap, rev, tw_ops)
+
+
 def solve_sparse_ref(n, i, j, cap, rev, tw_ops):
     """The real reference BK on a general sparse graph: `tw_ops` = sequence of (nodes, src, snk) array triples replayed
     as add_tweights calls in order, then sum_edge(i[k], j[k], cap[k], rev[k]) in order (oracle/ref_driver.cpp).
     Returns (flow, mask uint8[n] with 1 = not SINK, maxflow seconds)."""
-    lib = _load_ref()
+    return _solve_sparse(_load_ref().bkref_sparse_solve, n, i, j, cap, rev, tw_ops)
+
+
+def _solve_sparse(fn, n, i, j, cap, rev, tw_ops):
     c_i32_p = ctypes.POINTER(ctypes.c_int32)
-    lib.bkref_sparse_solve.restype = ctypes.c_int
-    lib.bkref_sparse_solve.argtypes = [ctypes.c_int, ctypes.c_int64, c_i32_p, c_i32_p, _c_double_p, _c_double_p,
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int, ctypes.c_int64, c_i32_p, c_i32_p, _c_double_p, _c_double_p,
                                        ctypes.c_int64, c_i32_p, _c_double_p, _c_double_p, _c_u8_p, _c_double_p,
                                        _c_double_p]
     ei = numpy.ascontiguousarray(i, dtype=numpy.int32)
@@ -155,9 +177,9 @@ def solve_sparse_ref(n, i, j, cap, rev, tw_ops):
     mask = numpy.empty(int(n), dtype=numpy.uint8)
     flow = ctypes.c_double(0)
     secs = ctypes.c_double(0)
-    rc = lib.bkref_sparse_solve(int(n), ei.size, ei.ctypes.data_as(c_i32_p), ej.ctypes.data_as(c_i32_p), _dptr(ec), _dptr(er),
+    rc = fn(int(n), ei.size, ei.ctypes.data_as(c_i32_p), ej.ctypes.data_as(c_i32_p), _dptr(ec), _dptr(er),
                                 tn.size, tn.ctypes.data_as(c_i32_p), _dptr(ts), _dptr(tk),
                                 mask.ctypes.data_as(_c_u8_p), ctypes.byref(flow), ctypes.byref(secs))
     if rc != 0:
-        raise RuntimeError("bkref_sparse_solve failed (%d)" % rc)
+        raise RuntimeError("sparse BK solve failed (%d)" % rc)
     return flow.value, mask, secs.value

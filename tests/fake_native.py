@@ -97,7 +97,7 @@ class FakeSparseGraph:
 
     def _solve(self):
         if self.result is None:
-            flow, mask, _ = solvers.solve_sparse_ref(self.n, self.e[0], self.e[1], self.e[2], self.e[3], self.tw)
+            flow, mask, _ = solvers.solve_sparse(self.n, self.e[0], self.e[1], self.e[2], self.e[3], self.tw)
             self.result = (flow, mask)
         return self.result
 

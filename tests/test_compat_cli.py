@@ -146,11 +146,9 @@ def test_own_label_cli_matches_oracle(tmp_path):
         lab_xyz = relabel(numpy.ascontiguousarray(regions.astype(numpy.int32)).T)     # what the CLI cut: x,y,z order
     finally:
         sys.path.remove(COMPAT)
-    if not solvers.have_ref():
-        pytest.skip("oracle/_ref not built")
     g_xyz, fg_xyz, bg_xyz = grad.T, vol["fg"].T, vol["bg"].T
     i, j, w, wr = elt.stawiaski_calls(lab_xyz, g_xyz)
     fgr, bgr = elt.marker_regions(lab_xyz, fg_xyz), elt.marker_regions(lab_xyz, bg_xyz)
     tw = [(fgr, numpy.full(fgr.size, 65535.0), numpy.zeros(fgr.size)), (bgr, numpy.zeros(bgr.size), numpy.full(bgr.size, 65535.0))]
-    _, rmask, _ = solvers.solve_sparse_ref(int(lab_xyz.max()), i, j, w, wr, tw)
+    _, rmask, _ = solvers.solve_sparse(int(lab_xyz.max()), i, j, w, wr, tw)
     assert numpy.array_equal(numpy.asarray(mask_xyz).astype(numpy.uint8), rmask[lab_xyz - 1])

@@ -190,13 +190,12 @@ def test_supervoxel_volume_vs_oracle_and_bk():
     flow = g.maxflow()
     mask = g.get_mask()
     assert 0 < int(mask.sum()) < mask.size
-    if solvers.have_ref():
-        n = int(lab.max())
-        fgr, bgr = elt.marker_regions(lab, fg), elt.marker_regions(lab, bg)
-        tw = [(fgr, numpy.full(fgr.size, 65535.0), numpy.zeros(fgr.size)), (bgr, numpy.zeros(bgr.size), numpy.full(bgr.size, 65535.0))]
-        rflow, rmask, _ = solvers.solve_sparse_ref(n, oi, oj, ow, owr, tw)
-        assert numpy.array_equal(mask, rmask)
-        assert flow == pytest.approx(rflow, rel=1e-9)
+    n = int(lab.max())
+    fgr, bgr = elt.marker_regions(lab, fg), elt.marker_regions(lab, bg)
+    tw = [(fgr, numpy.full(fgr.size, 65535.0), numpy.zeros(fgr.size)), (bgr, numpy.zeros(bgr.size), numpy.full(bgr.size, 65535.0))]
+    rflow, rmask, _ = solvers.solve_sparse(n, oi, oj, ow, owr, tw)
+    assert numpy.array_equal(mask, rmask)
+    assert flow == pytest.approx(rflow, rel=1e-9)
     # means term on the same volume: device means and adjacency against the oracle
     r = Recorder()
     el.boundary_difference_of_means(r, lab, img)
@@ -224,7 +223,6 @@ def random_graph(rng, n, m, integer):
     return i, j, cap, rev, src, snk, fg, bg
 
 
-@pytest.mark.skipif(not solvers.have_ref(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("seed", range(10))
 def test_general_sparse_graph_vs_reference_bk(seed):
     """GCGraph used the way tests/graphcut_/graph.py uses it: arbitrary node pairs, element-wise and bulk setters."""
@@ -251,7 +249,7 @@ def test_general_sparse_graph_vs_reference_bk(seed):
     assert g.is_sparse
     tw = [(numpy.arange(n), src, snk), (fg, numpy.full(fg.size, 65535.0), numpy.zeros(fg.size)),
           (bg, numpy.zeros(bg.size), numpy.full(bg.size, 65535.0))]
-    rflow, rmask, _ = solvers.solve_sparse_ref(n, i, j, cap, rev, tw)
+    rflow, rmask, _ = solvers.solve_sparse(n, i, j, cap, rev, tw)
     flow = g.maxflow()
     assert numpy.array_equal(g.get_mask(), rmask)
     if integer:

@@ -14,7 +14,6 @@ from oracle import solvers  # noqa: E402
 import fake_native  # noqa: E402
 import test_gpu_labels as T  # noqa: E402
 
-pytestmark = pytest.mark.skipif(not solvers.have_ref(), reason="oracle/_ref not built")
 
 
 @pytest.fixture(autouse=True)

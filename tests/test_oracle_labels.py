@@ -99,3 +99,63 @@ def test_whole_cut_through_reference_bk(nm, tag):
         assert flow == pytest.approx(want, rel=1e-12, abs=1e-300)
     else:
         assert flow == want
+
+
+# ---- the BK restatement for general graphs (oracle/bk_sparse.c) ------------------------------------------------------
+def _random_graph(rng, n, m, integer):
+    i = rng.integers(0, n, size=m)
+    j = rng.integers(0, n, size=m)
+    keep = i != j
+    i, j = i[keep], j[keep]
+    if integer:
+        cap = rng.integers(0, 20, size=i.size).astype(float)      # zero capacities are legal for sum_edge (graph.h:461)
+        rev = rng.integers(0, 20, size=i.size).astype(float)
+        src = rng.integers(0, 30, size=n).astype(float)
+        snk = rng.integers(0, 30, size=n).astype(float)
+    else:
+        cap = rng.uniform(1e-3, 2.0, size=i.size)
+        rev = rng.uniform(1e-3, 2.0, size=i.size)
+        src = rng.uniform(0, 3.0, size=n)
+        snk = rng.uniform(-0.5, 3.0, size=n)                        # negative t-weights are legal (graph.py:462-498)
+    fg = rng.choice(n, size=max(1, n // 20), replace=False)
+    bg = rng.choice(n, size=max(1, n // 20), replace=False)
+    tw = [(numpy.arange(n), src, snk), (fg, numpy.full(fg.size, 65535.0), numpy.zeros(fg.size)),
+          (bg, numpy.zeros(bg.size), numpy.full(bg.size, 65535.0))]
+    return i, j, cap, rev, tw
+
+
+@pytest.mark.skipif(not solvers.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed", range(40))
+def test_sparse_port_equals_reference_bk_bit_for_bit(seed):
+    rng = numpy.random.default_rng(1000 + seed)
+    n = int(rng.integers(2, 600))
+    m = int(rng.integers(1, 8 * n))
+    i, j, cap, rev, tw = _random_graph(rng, n, m, seed % 2 == 0)
+    rflow, rmask, _ = solvers.solve_sparse_ref(n, i, j, cap, rev, tw)
+    pflow, pmask, _ = solvers.solve_sparse_port(n, i, j, cap, rev, tw)
+    assert pflow == rflow                      # same arc order => same augmentations => same float64 flow
+    assert numpy.array_equal(pmask, rmask)
+
+
+@pytest.mark.parametrize("tag", ["cut_stawiaski", "cut_means", "cut_directed_atlas"])
+@pytest.mark.parametrize("nm", FULL)
+def test_sparse_port_on_golden_region_graphs(nm, tag):
+    n, i, j, cap, rev, tw = label_problem(nm, tag)
+    flow, mask, _ = solvers.solve_sparse_port(n, i, j, cap, rev, tw)
+    assert numpy.array_equal(mask, G[nm + "/" + tag + "_mask"])
+    want = float(G[nm + "/" + tag + "_flow"])
+    if tag == "cut_means":
+        assert flow == pytest.approx(want, rel=1e-12, abs=1e-300)
+    else:
+        assert flow == want
+
+
+def test_sparse_port_reference_diamond():
+    """lib/maxflow/src/sum_edge_test.py:20-37: flow 2, and 4 once every edge was summed a second time."""
+    e = [(0, 1), (0, 2), (1, 3), (2, 3)]
+    tw = [(numpy.asarray([0, 3]), numpy.asarray([99.0, 0.0]), numpy.asarray([0.0, 99.0]))]
+    i, j = numpy.asarray([a for a, _ in e]), numpy.asarray([b for _, b in e])
+    flow, mask, _ = solvers.solve_sparse_port(4, i, j, numpy.ones(4), numpy.zeros(4), tw)
+    assert flow == 2.0
+    flow, mask, _ = solvers.solve_sparse_port(4, numpy.tile(i, 2), numpy.tile(j, 2), numpy.ones(8), numpy.zeros(8), tw)
+    assert flow == 4.0 and mask.tolist() == [1, 1, 1, 0]

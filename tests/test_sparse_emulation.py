@@ -14,7 +14,6 @@ sys.path.insert(0, os.path.dirname(HERE))
 from oracle import energy_label_terms as elt  # noqa: E402
 from oracle import solvers  # noqa: E402
 
-pytestmark = pytest.mark.skipif(not solvers.have_ref(), reason="oracle/_ref not built")
 
 
 @pytest.fixture(scope="module")
@@ -93,7 +92,7 @@ def test_random_sparse_graphs_match_reference_bk(emu, seed):
     m = int(rng.integers(1, 6 * n))
     integer = seed % 2 == 0
     i, j, cap, rev, tw = random_graph(rng, n, m, integer)
-    flow, mask, _ = solvers.solve_sparse_ref(n, i, j, cap, rev, tw)
+    flow, mask, _ = solvers.solve_sparse(n, i, j, cap, rev, tw)
     e, got = run_emu(emu, n, i, j, cap, rev, tw, steps=1 + seed % 4, sweeps=1 + 5 * (seed % 3))
     assert numpy.array_equal(got, mask)
     if integer:
@@ -108,7 +107,7 @@ def test_isolated_and_terminal_only_nodes(emu):
     i, j = numpy.asarray([3]), numpy.asarray([4])
     cap, rev = numpy.asarray([2.0]), numpy.asarray([0.5])
     tw = [(numpy.asarray([0, 1, 3, 4]), numpy.asarray([5.0, 0.0, 7.0, 0.0]), numpy.asarray([0.0, 4.0, 0.0, 9.0]))]
-    flow, mask, _ = solvers.solve_sparse_ref(n, i, j, cap, rev, tw)
+    flow, mask, _ = solvers.solve_sparse(n, i, j, cap, rev, tw)
     e, got = run_emu(emu, n, i, j, cap, rev, tw)
     assert numpy.array_equal(got, mask) and e == flow == 2.0
     assert got.tolist() == [1, 0, 1, 1, 0]

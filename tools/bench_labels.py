@@ -77,11 +77,10 @@ def cpu_run(n, cell):
     t1 = time.perf_counter()
     out = dict(size=n, cell=cell, voxels=int(lab.size), regions=int(lab.max()), border_pairs=int(i.size), terms_numpy_s=t1 - t0,
                reference_python_loop_s_estimate=1e-6 * i.size)
-    if solvers.have_ref():
-        tw = [(fgr, numpy.full(fgr.size, 65535.0), numpy.zeros(fgr.size)), (bgr, numpy.zeros(bgr.size), numpy.full(bgr.size, 65535.0))]
-        t2 = time.perf_counter()
-        flow, mask, secs = solvers.solve_sparse_ref(int(lab.max()), i, j, w, wr, tw)
-        out.update(bk_fill_and_maxflow_s=time.perf_counter() - t2, bk_maxflow_s=secs, energy=flow)
+    tw = [(fgr, numpy.full(fgr.size, 65535.0), numpy.zeros(fgr.size)), (bgr, numpy.zeros(bgr.size), numpy.full(bgr.size, 65535.0))]
+    t2 = time.perf_counter()
+    flow, mask, secs = solvers.solve_sparse(int(lab.max()), i, j, w, wr, tw)
+    out.update(bk_fill_and_maxflow_s=time.perf_counter() - t2, bk_maxflow_s=secs, energy=flow)
     out["mvox_per_s"] = lab.size / (out["terms_numpy_s"] + out.get("bk_fill_and_maxflow_s", 0.0)) / 1e6
     return out
 
