@@ -5,7 +5,7 @@ import medpy_b200.graphcut as _gc
 from medpy_b200.graphcut import *  # noqa: F401,F403
 from medpy_b200.graphcut import (GCGraph, energy_label, energy_voxel, graph_from_labels, graph_from_voxels,  # noqa: F401
                                  maxflow, split_marker)
-from medpy_b200.graphcut import generate, graph, wrapper  # noqa: F401
+from medpy_b200.graphcut import generate, graph, wrapper, write  # noqa: F401
 
-for _name in ("energy_voxel", "energy_label", "maxflow", "generate", "graph", "wrapper"):
+for _name in ("energy_voxel", "energy_label", "maxflow", "generate", "graph", "wrapper", "write"):
     sys.modules[__name__ + "." + _name] = getattr(_gc, _name)

@@ -11,6 +11,78 @@ import numpy
 from .maxflow import GraphDouble
 
 
+class Graph(object):
+    """The reference's plain-Python graph description (medpy/graphcut/graph.py:29-265): a record of node count,
+    source / sink node lists and weight dictionaries with node ids starting at 1, consumed by ``graph_to_dimacs``.
+    It holds no solver; use ``GCGraph`` to cut a graph."""
+
+    MAX = 65535
+    """The maximum value a weight can take (graph.py:45-50)."""
+
+    def __init__(self):
+        self._node_count = 0
+        self._source_nodes = []
+        self._sink_nodes = []
+        self._nweights = {}
+        self._tweights = {}
+
+    def set_nodes(self, nodes):
+        """Number of nodes, terminals excluded (graph.py:58-66)."""
+        self._node_count = int(nodes)
+
+    def set_source_nodes(self, source_nodes):
+        """Tie nodes to the source: t-weight (MAX, 0) each (graph.py:68-85)."""
+        self._source_nodes = list(source_nodes)
+        self._tweights.update((v, (self.MAX, 0)) for v in self._source_nodes)
+
+    def set_sink_nodes(self, sink_nodes):
+        """Tie nodes to the sink: t-weight (0, MAX) each (graph.py:87-104)."""
+        self._sink_nodes = list(sink_nodes)
+        self._tweights.update((v, (0, self.MAX)) for v in self._sink_nodes)
+
+    def set_nweights(self, nweights):
+        """{(node, node): (weight, reverse weight)}; replaces what was set before (graph.py:106-113)."""
+        self._nweights = nweights
+
+    def add_tweights(self, tweights):
+        """{node: (weight to source, weight to sink)}; overrides entries set before, markers included (graph.py:115-128)."""
+        self._tweights.update(tweights)
+
+    def get_node_count(self):
+        return self._node_count
+
+    def get_nodes(self):
+        return list(range(1, self._node_count + 1))
+
+    def get_source_nodes(self):
+        return self._source_nodes
+
+    def get_sink_nodes(self):
+        return self._sink_nodes
+
+    def get_edges(self):
+        return list(self._nweights.keys())
+
+    def get_nweights(self):
+        return self._nweights
+
+    def get_tweights(self):
+        """Only the t-weights set so far (graph.py:210-222)."""
+        return self._tweights
+
+    def inconsistent(self):
+        """False, or the list of problems: ids above the node count, edges stored in both directions (graph.py:224-265)."""
+        found = []
+        found += ["Node {} in t-weights but not in nodes.".format(v) for v in self._tweights if not v <= self._node_count]
+        found += ["Node {} in s-nodes but not in nodes.".format(v) for v in self._source_nodes if not v <= self._node_count]
+        found += ["Node {} in t-nodes but not in nodes.".format(v) for v in self._sink_nodes if not v <= self._node_count]
+        for e in self._nweights:
+            found += ["Node {} in edge {} but not in nodes.".format(v, e) for v in e[:2] if not v <= self._node_count]
+            if (e[1], e[0]) in self._nweights:
+                found.append("The reversed edges of {} is also in the n-weights.".format(e))
+        return found if found else False
+
+
 class GCGraph:
     """Validated wrapper over the lattice graph, API-compatible with the reference's GCGraph."""
 
