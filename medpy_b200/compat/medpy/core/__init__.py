@@ -4,8 +4,7 @@ import logging
 import sys
 
 
-class ArgumentError(Exception):
-    """Raised for invalid command line arguments."""
+from medpy_b200.errors import ArgumentError  # noqa: F401,E402  (one class for the host layer and the shim)
 
 
 class ImageLoadingError(Exception):

@@ -14,7 +14,9 @@ GCGraphTest, tests/graphcut_/energy_label.py:189-210), and -- for whole ``graph_
 aliases it to ``inspect.getfullargspec`` in THIS process (same first field) so that the function runs at all; nothing
 under /root/reference is touched.  The light-to-dark branch of boundary_stawiaski_directed (directedness >= 0) raises
 TypeError in the reference (energy_label.py:281: a fifth parameter nobody passes), so only directedness < 0 has
-golden vectors.
+golden vectors.  ``graphcut_split`` (wrapper.py:72-225) needs two more crutches, again in this process only: an empty
+``SimpleITK`` module (medpy.filter imports medpy.io at module level) and ``functools.reduce`` under the name the
+function expects (wrapper.py:145 calls the Python-2 builtin ``reduce``).
 """
 import inspect
 import os
@@ -135,6 +137,34 @@ def main():
                     seg = numpy.asarray([0 if g.what_segment(v) == g.termtype.SINK else 1 for v in range(nreg)], dtype=numpy.uint8)
                     store[nm + "/" + tag + "_flow"] = numpy.asarray(flow)
                     store[nm + "/" + tag + "_mask"] = seg
+    # graphcut_split / graphcut_stawiaski (wrapper.py:72-329): 8 overlapping sub-volumes, every one holding both markers
+    import types
+    sys.modules.setdefault("SimpleITK", types.ModuleType("SimpleITK"))   # medpy.filter -> medpy.io imports it at module level; unused here
+    import functools
+    import medpy.graphcut.wrapper as ref_wrapper
+    if not hasattr(ref_wrapper, "reduce"):
+        ref_wrapper.reduce = functools.reduce      # wrapper.py:145 uses the Python-2 builtin: NameError on Python 3 otherwise
+    from medpy.graphcut.wrapper import graphcut_split, graphcut_stawiaski
+    shape = (24, 22, 20)
+    lab = supervoxels(shape, 60, 77)
+    rng = numpy.random.default_rng(78)
+    grad = numpy.abs(rng.normal(0, 20, size=shape) + 40 * (lab % 3 == 0)).astype(numpy.float32)
+    fg = numpy.zeros(shape, bool)
+    bg = numpy.zeros(shape, bool)
+    for corner in numpy.ndindex(2, 2, 2):
+        origin = [c * (s // 2) for c, s in zip(corner, shape)]
+        fg[tuple(b + s // 4 for b, s in zip(origin, shape))] = True
+        bg[tuple(b + 1 for b in origin)] = True
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        whole = graphcut_stawiaski((lab.copy(), grad, fg, bg))     # the only calling form that works in the reference
+        split = graphcut_split(graphcut_stawiaski, lab.copy(), grad, fg, bg, 10, 3, 2)
+    store["split/label"] = lab
+    store["split/gradient"] = grad
+    store["split/fg"] = fg
+    store["split/bg"] = bg
+    store["split/whole_mask"] = numpy.asarray(whole, dtype=numpy.uint8)
+    store["split/split_mask"] = numpy.asarray(split, dtype=numpy.uint8)
     store["names"] = numpy.asarray(names)
     numpy.savez_compressed(os.path.join(HERE, "golden_labels_v1.npz"), **store)
     print("wrote", len(names), "cases")

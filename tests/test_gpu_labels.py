@@ -203,6 +203,26 @@ def test_supervoxel_volume_vs_oracle_and_bk():
     _assert_edges(r.n, {(int(x), int(y)): (u, u) for x, y, u in zip(mi, mj, mw)}, True)
 
 
+def test_wrapper_functions_vs_reference():
+    """graphcut_stawiaski on the whole volume and graphcut_split over 8 overlapping sub-volumes (wrapper.py:72-329)."""
+    gc = _gc()
+    from medpy_b200.errors import ArgumentError
+    lab, grad, fg, bg = G["split/label"], G["split/gradient"], G["split/fg"], G["split/bg"]
+    whole = gc.graphcut_stawiaski(lab, grad, fg, bg)
+    assert whole.dtype == numpy.bool_ and numpy.array_equal(whole, G["split/whole_mask"].astype(bool))
+    assert numpy.array_equal(gc.graphcut_stawiaski((lab, grad, fg, bg)), whole)          # the tuple form the pool used
+    split = gc.graphcut_split(gc.graphcut_stawiaski, lab, grad, fg, bg, 10, 3, 2)
+    assert numpy.array_equal(split, G["split/split_mask"].astype(bool))
+    with pytest.raises(ArgumentError):
+        gc.graphcut_split(gc.graphcut_stawiaski, lab, grad, fg, bg, 9, 3)
+    with pytest.raises(ArgumentError):
+        gc.graphcut_split(gc.graphcut_stawiaski, lab, grad, fg, bg, 10, 10)
+    with pytest.raises(ArgumentError):
+        gc.graphcut_split(gc.graphcut_stawiaski, lab, grad[1:], fg, bg, 10, 3)
+    with pytest.raises(ArgumentError):
+        gc.graphcut_subprocesses(gc.graphcut_stawiaski, [], -1)
+
+
 def random_graph(rng, n, m, integer):
     i = rng.integers(0, n, size=m)
     j = rng.integers(0, n, size=m)

@@ -49,3 +49,7 @@ def test_general_sparse_graph_glue(seed):
 
 def test_sparse_fixture_glue():
     T.test_sparse_graph_reference_fixture_and_reset()
+
+
+def test_wrapper_functions_glue():
+    T.test_wrapper_functions_vs_reference()
