@@ -152,3 +152,40 @@ def test_own_label_cli_matches_oracle(tmp_path):
     tw = [(fgr, numpy.full(fgr.size, 65535.0), numpy.zeros(fgr.size)), (bgr, numpy.zeros(bgr.size), numpy.full(bgr.size, 65535.0))]
     _, rmask, _ = solvers.solve_sparse(int(lab_xyz.max()), i, j, w, wr, tw)
     assert numpy.array_equal(numpy.asarray(mask_xyz).astype(numpy.uint8), rmask[lab_xyz - 1])
+
+
+OTHER_LABEL_CLIS = [
+    ("medpy_graphcut_label_w_regional.py", lambda p, out: [p["grad"], p["regions"], p["markers"], out, "--regional", "atlas",
+                                                            "--radditional", p["atlas"], "--alpha", "0.2", "-f"]),
+    ("medpy_graphcut_label_wsplit.py", lambda p, out: [p["grad"], p["regions"], p["markers"], out, "-f"]),
+]
+# (bin/medpy_graphcut_label_bgreduced.py cannot run on numpy >= 1.13 at all: it subtracts boolean arrays in its own
+#  pre-processing, :217, long before it reaches the graph cut.)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_LABEL_CLI), reason="reference tree not present")
+@pytest.mark.parametrize("script,argv", OTHER_LABEL_CLIS, ids=[c[0] for c in OTHER_LABEL_CLIS])
+def test_other_reference_label_clis_run_unchanged_up_to_the_device(tmp_path, script, argv):
+    """The remaining region-cut scripts of the reference, in place and unmodified: regional_atlas + boundary term
+    (w_regional), graphcut_split(graphcut_stawiaski, ...) (wsplit).
+    Everything they import resolves in the shim; without a GPU they stop where the product refuses to run on a CPU."""
+    import torch
+    sys.path.insert(0, COMPAT)
+    try:
+        from medpy.io import save, Header
+    finally:
+        sys.path.remove(COMPAT)
+    vol, regions, grad, paths = _write_label_case(tmp_path, shape=(24, 22, 20))
+    atlas = (1.0 / (1.0 + numpy.exp(-(vol["image"].astype(numpy.float64) - 50.0) / 15.0))).astype(numpy.float32)
+    paths["atlas"] = str(tmp_path / "atlas.mha")
+    save(numpy.ascontiguousarray(atlas).T, paths["atlas"], Header(spacing=(1.0, 1.0, 1.0), offset=(0.0, 0.0, 0.0)), True)
+    out = str(tmp_path / "out.mha")
+    env = dict(os.environ, PYTHONPATH=COMPAT + os.pathsep + ROOT, PYTHONDONTWRITEBYTECODE="1")
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(REF_LABEL_CLI), script)] + argv(paths, out),
+                       env=env, capture_output=True, text=True, timeout=300)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert os.path.exists(out)
+    else:
+        assert r.returncode != 0
+        assert "no CPU" in r.stderr or "CUDA" in r.stderr, r.stderr[-3000:]
