@@ -139,3 +139,32 @@ def test_pairwise_sum_equals_numpy_sum(tmp_path):
         a64 = rng.normal(0, 100, n)
         assert numpy.float32(lib.emu_pairwise_f32(a32.ctypes.data, n)) == numpy.sum(a32), n
         assert lib.emu_pairwise_f64(a64.ctypes.data, n) == numpy.sum(a64), n
+
+
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+_graphs = st.integers(2, 14).flatmap(lambda n: st.tuples(
+    st.just(n),
+    st.lists(st.tuples(st.integers(0, n - 1), st.integers(0, n - 1), st.integers(0, 6), st.integers(0, 6)), min_size=0, max_size=50),
+    st.lists(st.tuples(st.integers(0, n - 1), st.integers(-3, 8), st.integers(-3, 8)), min_size=1, max_size=24),
+    st.integers(1, 4), st.integers(1, 9)))
+
+
+@settings(max_examples=300, deadline=None)
+@given(_graphs)
+def test_small_integer_graphs_with_ties_match_bk_exactly(emu, g):
+    """Small integer capacities make ties (several minimum cuts, saturated and zero arcs, negative t-weights, repeated
+    add_tweights on one node) the rule: the product's algorithm must still return BK's flow and BK's sink set."""
+    n, edges, tws, steps, sweeps = g
+    edges = [e for e in edges if e[0] != e[1]]
+    i = numpy.asarray([e[0] for e in edges], dtype=numpy.int64)
+    j = numpy.asarray([e[1] for e in edges], dtype=numpy.int64)
+    cap = numpy.asarray([e[2] for e in edges], dtype=float)
+    rev = numpy.asarray([e[3] for e in edges], dtype=float)
+    tw = [(numpy.asarray([t[0]]), numpy.asarray([float(t[1])]), numpy.asarray([float(t[2])])) for t in tws]
+    flow, mask, _ = solvers.solve_sparse(n, i, j, cap, rev, tw)
+    if i.size == 0:
+        i, j, cap, rev = numpy.asarray([0]), numpy.asarray([1]), numpy.asarray([0.0]), numpy.asarray([0.0])
+    e, got = run_emu(emu, n, i, j, cap, rev, tw, steps=steps, sweeps=sweeps)
+    assert e == flow
+    assert numpy.array_equal(got, mask)
