@@ -182,16 +182,34 @@ class GraphDouble:
                 self._nat().add_nweights_dense(op[1], op[2].reshape(self._shape), op[3].reshape(self._shape))
 
     # ------------------------------------------------------------------ bulk term entry points (used by energy_voxel)
+    def _lattice_term(self):
+        """A whole-lattice term is about to be applied: a shape-less graph that takes one stays the 1-D chain it was
+        created as (its journal cannot describe device-side terms, so it can no longer move to the sparse backend)."""
+        if self._sp is None:
+            self._journal = None
+
     def add_regional_probability(self, prob, alpha, compute_f32):
+        self._lattice_term()
         self._flush()
         self._dirty()
         self._nat().add_regional_probability(self._positive_strides(prob), float(alpha), bool(compute_f32))
 
     def add_tweights_dense(self, src, snk):
-        self._flush()
-        self._dirty()
+        """add_tweights(v, src[v], snk[v]) for every node (GCGraph.set_tweights_all, graph.py:532-552)."""
+        if self._sp is not None:
+            return self._sp.add_tweights_bulk(None, numpy.ravel(src), numpy.ravel(snk))
         src = numpy.ascontiguousarray(src, dtype=numpy.float64).reshape(self._shape)
         snk = numpy.ascontiguousarray(snk, dtype=numpy.float64).reshape(self._shape)
+        if self._journal is not None:
+            # shape-less graph: staged like the element-wise calls (no device needed yet) and journaled node-wise, so a
+            # later move to the sparse backend can replay it
+            self._journal.append(("T", numpy.arange(self._n), src.ravel().copy(), snk.ravel().copy()))
+            self._close_tweight_batch()
+            self._pending.append(("tw", src.ravel().copy(), snk.ravel().copy()))
+            self._dirty()
+            return
+        self._flush()
+        self._dirty()
         self._nat().add_tweights_dense(src, snk)
 
     @staticmethod
@@ -205,16 +223,19 @@ class GraphDouble:
         return a
 
     def add_markers(self, fg, bg):
+        self._lattice_term()
         self._flush()
         self._dirty()
         self._nat().add_markers(self._positive_strides(fg), self._positive_strides(bg))
 
     def add_boundary(self, kind, image, sigma, spacing, norm):
+        self._lattice_term()
         self._flush()
         self._dirty()
         self._nat().add_boundary(int(kind), self._positive_strides(image), float(sigma), spacing, float(norm))
 
     def add_nweights_dense(self, axis, fwd, bwd):
+        self._lattice_term()
         self._flush()
         self._dirty()
         self._nat().add_nweights_dense(int(axis), fwd, bwd)

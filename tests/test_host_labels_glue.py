@@ -53,3 +53,22 @@ def test_sparse_fixture_glue():
 
 def test_wrapper_functions_glue():
     T.test_wrapper_functions_vs_reference()
+
+
+def test_set_tweights_all_on_general_graphs():
+    """GCGraph.set_tweights_all (graph.py:532-552) on a sparse graph, and on a shape-less graph BEFORE it turns sparse."""
+    import numpy
+    from medpy_b200.graphcut import GCGraph
+    from oracle import solvers as S
+    tw = numpy.asarray([[5.0, 0.0], [0.0, 1.0], [0.0, 0.0], [0.0, 4.0]])
+    edges = [(0, 2, 3.0, 1.0), (2, 3, 2.0, 2.0), (0, 1, 0.5, 0.5)]
+    want = S.solve_sparse(4, [e[0] for e in edges], [e[1] for e in edges], [e[2] for e in edges], [e[3] for e in edges],
+                          [(numpy.arange(4), tw[:, 0], tw[:, 1])])
+    for sparse_first in (True, False):
+        g = GCGraph(4, 3, sparse=True if sparse_first else None)
+        g.set_tweights_all(tw)                      # journaled when the graph is still a chain
+        for a, b, c, d in edges:
+            g.set_nweight(a, b, c, d)               # (0, 2) is no chain neighbour -> sparse backend
+        assert g.get_graph().is_sparse
+        assert g.get_graph().maxflow() == want[0]
+        assert numpy.array_equal(g.get_graph().get_mask(), want[1])
