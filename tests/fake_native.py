@@ -128,3 +128,119 @@ class FakeSparseGraph:
 
     def stats(self):
         return dict(n_nodes=self.n, global_relabels=0, push_sweeps=0, kernel_launches=0, ms_solve=0.0)
+
+
+# ---- lattice double (``_mgc.Graph``) ------------------------------------------------------------------------------------
+from oracle import energy_terms as et  # noqa: E402
+
+_KINDS = ["difference_linear", "difference_exponential", "difference_division", "difference_power",
+          "maximum_linear", "maximum_exponential", "maximum_division", "maximum_power"]
+
+
+class FakeGraph:
+    """The dense-lattice native class on top of oracle/energy_terms.py + oracle/bk_lattice.c."""
+
+    def __init__(self, shape, device=-1):
+        self.shape = [int(s) for s in shape]
+        self.n = int(numpy.prod(self.shape))
+        self.reset()
+
+    def reset(self):
+        self.wf = [numpy.zeros(self.n) for _ in self.shape]
+        self.wb = [numpy.zeros(self.n) for _ in self.shape]
+        self.tr = numpy.zeros(self.n)
+        self.flow = 0.0
+        self.result = None
+
+    def set_option(self, option, value):
+        pass
+
+    def check_deferred(self):
+        pass
+
+    def set_stream(self, s):
+        pass
+
+    def synchronize(self):
+        pass
+
+    def add_regional_probability(self, prob, alpha, compute_f32):
+        prob = numpy.asarray(prob)
+        assert bool(compute_f32) == (prob.dtype == numpy.float32)
+        src, snk = et.regional_probability_tweights(prob, alpha)
+        self.flow = et.add_tweights_pass(self.tr, self.flow, src, snk)
+        self.result = None
+
+    def add_tweights_dense(self, src, snk):
+        self.flow = et.add_tweights_pass(self.tr, self.flow, numpy.asarray(src, dtype=float).ravel(), numpy.asarray(snk, dtype=float).ravel())
+        self.result = None
+
+    def add_markers(self, fg, bg):
+        if fg is not None and numpy.asarray(fg).any():
+            self.flow = et.add_tweights_pass(self.tr, self.flow, 65535.0, 0.0, where=numpy.asarray(fg).ravel().astype(bool))
+        if bg is not None and numpy.asarray(bg).any():
+            self.flow = et.add_tweights_pass(self.tr, self.flow, 0.0, 65535.0, where=numpy.asarray(bg).ravel().astype(bool))
+        self.result = None
+
+    def add_boundary(self, kind, image, sigma, spacing, norm):
+        image = numpy.asarray(image)
+        w = et.boundary_weights(_KINDS[kind], image, sigma, spacing if spacing else False)
+        for arr in w:
+            if (arr <= 0).any():
+                raise ValueError("Negative or zero weights are not allowed.")
+        for d, full in enumerate(et.dense_axis_arrays(tuple(self.shape), w)):
+            self.wf[d] += full
+            self.wb[d] += full
+        self.result = None
+
+    def add_nweights_dense(self, axis, fwd, bwd):
+        fwd, bwd = numpy.asarray(fwd, dtype=float).ravel(), numpy.asarray(bwd, dtype=float).ravel()
+        if (fwd < 0).any() or (bwd < 0).any():
+            raise ValueError("Negative or zero weights are not allowed.")
+        stride = int(numpy.prod(self.shape[axis + 1:]))
+        last = (numpy.arange(self.n) // stride) % self.shape[axis] == self.shape[axis] - 1
+        self.wf[axis] += numpy.where(last, 0.0, fwd)
+        self.wb[axis] += numpy.where(last, 0.0, bwd)
+        self.result = None
+
+    def _solve(self):
+        if self.result is None:
+            prob = dict(shape=tuple(self.shape), wf=self.wf, wb=self.wb, tr=self.tr.copy(), flow_const=self.flow)
+            flow, mask, _ = solvers.solve_port(prob)
+            self.result = (flow, mask)
+        return self.result
+
+    def maxflow(self):
+        return self._solve()[0]
+
+    def get_mask(self):
+        return self._solve()[1].copy()
+
+    def what_segment(self, i):
+        return 0 if self._solve()[1].flat[int(i)] else 1
+
+    def _axis(self, i, j):
+        lo, d = min(i, j), abs(i - j)
+        for axis in range(len(self.shape)):
+            stride = int(numpy.prod(self.shape[axis + 1:]))
+            if d == stride and self.shape[axis] > 1 and (lo // stride) % self.shape[axis] < self.shape[axis] - 1:
+                return axis, lo
+        return None, lo
+
+    def get_edge(self, i, j):
+        axis, lo = self._axis(int(i), int(j))
+        if axis is None:
+            return 0.0
+        return float(self.wf[axis][lo] if i < j else self.wb[axis][lo])
+
+    def get_trcap(self, i):
+        return float(self.tr[int(i)])
+
+    def get_node_num(self):
+        return self.n
+
+    def get_arc_num(self):
+        return 2 * sum((self.n // s) * (s - 1) for s in self.shape if s > 1)
+
+    def stats(self):
+        return dict(n_voxels=self.n, kernel_launches=0, push_sweeps=0, global_relabels=0, flow_const=self.flow)
