@@ -159,3 +159,14 @@ def test_sparse_port_reference_diamond():
     assert flow == 2.0
     flow, mask, _ = solvers.solve_sparse_port(4, numpy.tile(i, 2), numpy.tile(j, 2), numpy.ones(8), numpy.zeros(8), tw)
     assert flow == 4.0 and mask.tolist() == [1, 1, 1, 0]
+
+
+@pytest.mark.skipif(not (os.path.isdir("/root/reference/medpy") and solvers.have_ref()), reason="reference tree / pyshim not present")
+def test_label_oracle_fuzzed_against_the_live_reference():
+    """150 random label images (2-D..4-D, five image dtypes, F order, random alpha / directedness): every call the
+    reference issues equals the restatement's, bit for bit (tests/golden/fuzz_labels_against_reference.py)."""
+    import subprocess
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fuzz_labels_against_reference.py")
+    r = subprocess.run([sys.executable, script, "150", "7"], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, PYTHONDONTWRITEBYTECODE="1"))
+    assert r.returncode == 0 and "ok 150" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
