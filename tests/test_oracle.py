@@ -1,5 +1,7 @@
 """CPU tests: the oracle (oracle/energy_terms.py + oracle/bk_lattice.c) against the golden vectors
 produced by the unmodified reference, and against the real reference solver when oracle/_ref exists."""
+import os
+
 import numpy
 import pytest
 
@@ -85,3 +87,17 @@ def test_port_equals_real_reference_float_32cubed():
     f2, m2, _ = solvers.solve_ref(prob)
     assert f1 == f2 and numpy.array_equal(m1, m2)
     assert 0 < m1.sum() < m1.size
+
+
+@pytest.mark.skipif(not (os.path.isdir("/root/reference/medpy") and solvers.have_ref()), reason="reference tree / pyshim not present")
+def test_voxel_oracle_fuzzed_against_the_live_reference():
+    """120 random lattices (1-D..4-D, the eight boundary terms, five image dtypes, random sigma / spacing / regional term /
+    overlapping markers) through the reference's own graph_from_voxels: weights, t-links, flow and mask equal the
+    restatement's bit for bit; weight <= 0 ValueErrors occur in the same cases
+    (tests/golden/fuzz_voxels_against_reference.py)."""
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fuzz_voxels_against_reference.py")
+    r = subprocess.run([sys.executable, script, "120", "11"], capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, PYTHONDONTWRITEBYTECODE="1"))
+    assert r.returncode == 0 and "ok 120" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
