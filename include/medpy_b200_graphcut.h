@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MGC_ABI_VERSION 2
+#define MGC_ABI_VERSION 3
 #define MGC_MAX_NDIM 4
 
 /* status codes */
@@ -93,7 +93,7 @@ typedef struct mgc_stats {
     double ms_push;             /* device ms inside push/relabel sweeps (CUDA events around each batch)  */
     double ms_relabel;          /* device ms inside global-relabel kernels (init + relaxation sweeps)    */
     double ms_boundary;         /* device ms of the last boundary (n-link) kernel alone                  */
-    double ms_init;             /* device ms of the solver-state initialisation kernel (k_init_tile)     */
+    double ms_init;             /* device ms of the solver-state initialisation kernel (k_init_tile); 0 after a fused build */
 } mgc_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------- */
@@ -158,6 +158,39 @@ int mgc_add_boundary(mgc_graph* g, int32_t kind, const mgc_array* image, double 
  * ignored.  Accumulates like sum_edge (graph.h:456-480); 0 leaves a pair untouched, negative values ->
  * MGC_E_WEIGHT (the `<= 0` ValueError of GCGraph.set_nweight is raised by the host layer, graph.py:436-437). */
 int mgc_add_nweights_dense(mgc_graph* g, int32_t axis, const mgc_array* fwd, const mgc_array* bwd);
+
+/* ---- the whole graph of graph_from_voxels in one call -------------------------------------------------- */
+
+/* Everything graph_from_voxels puts into the graph (generate.py:159-172: regional term, boundary term, foreground
+ * markers, background markers) handed over at once.  On a fresh handle (create / mgc_reset, nothing added yet) of a
+ * 1-D..3-D lattice the terms are evaluated by ONE kernel pass (csrc/gc_build.cuh: n-link stencil + t-link replay +
+ * solver-state initialisation; the image block of every CTA is staged by a TMA box copy) instead of four passes
+ * over the lattice, and for contiguous host arrays the upload of z-chunk c+1 overlaps the build of chunk c.  The
+ * result is the graph mgc_add_regional_probability + mgc_add_boundary + mgc_add_markers would leave (same
+ * arithmetic per weight; the add_tweights constant is summed in a different, still fixed, order).  Anything else
+ * (4-D lattice, no boundary term, terms already present) runs those three calls in that order.
+ *   prob / fg / bg may be NULL; boundary_kind -1 = no boundary term; markers either as uint8 arrays (fg, bg) or
+ *   bit-packed over the C-order flat voxel index v: bit (v & 31) of word (v >> 5) (fg_bits, bg_bits, bits_mem).
+ * Weight verdict: MGC_E_WEIGHT from this call, or -- with MGC_OPT_DEFER_WEIGHT_CHECK -- from the next
+ * mgc_check / mgc_maxflow.  Host pointers are borrowed for the duration of the call only. */
+typedef struct mgc_voxel_terms {
+    const mgc_array* prob;   /* regional_probability_map input (energy_voxel.py:33-65) or NULL */
+    double alpha;
+    int32_t compute_dtype;   /* MGC_F32 / MGC_F64, see mgc_add_regional_probability */
+    int32_t boundary_kind;   /* MGC_BOUNDARY_* or -1 */
+    const mgc_array* image;
+    double sigma;
+    const double* spacing;   /* NULL: no distance weighting */
+    double norm;             /* linear terms: normaliser or NaN, see mgc_add_boundary */
+    const mgc_array* fg;     /* uint8 marker volumes or NULL */
+    const mgc_array* bg;
+    const uint32_t* fg_bits; /* bit-packed marker volumes or NULL */
+    const uint32_t* bg_bits;
+    int32_t bits_mem;        /* MGC_MEM_HOST / MGC_MEM_DEVICE of fg_bits / bg_bits */
+} mgc_voxel_terms;
+int mgc_build_voxel_graph(mgc_graph* g, const mgc_voxel_terms* terms);
+/* 1 if mgc_build_voxel_graph would take the single-pass path on a fresh state of this handle. */
+int mgc_can_fuse(const mgc_graph* g);
 
 /* ---- solve / read-out ----------------------------------------------------------------------------- */
 

@@ -9,6 +9,8 @@
 #include "gc_persist.cuh"
 #include "gc_tma.cuh"
 #include "gc_tiles4.cuh"
+#include "gc_sweep.cuh"
+#include "gc_build.cuh"
 #include "gc_gradient.cuh"
 
 #include <cmath>
@@ -110,7 +112,7 @@ struct mgc_graph {
 
     State<double> S{};
     std::vector<Buf> owned_bufs;       // everything allocated from the pool
-    Buf scratch[3];                    // staged (contiguous) copies of input arrays
+    Buf scratch[5];                    // staged (contiguous) copies of input arrays: 0 prob/src, 1 fg/snk, 2 image, 4 bg
     Buf raw;                           // raw span of a strided host array
     uint8_t* mask_dev = nullptr;
     double* partials = nullptr;        // per-block partial sums
@@ -128,8 +130,9 @@ struct mgc_graph {
     // previous one; the host only waits for the COPY (its pointer is borrowed for the call), never for the kernel
     cudaStream_t up_stream = nullptr;
     cudaEvent_t ev_up = nullptr;
-    cudaEvent_t ev_slot[4] = {};       // main-stream point after which a staging slot may be overwritten
-    bool slot_used[4] = {false, false, false, false};
+    cudaEvent_t ev_slot[5] = {};       // main-stream point after which a staging slot may be overwritten (3 = raw span)
+    bool slot_used[5] = {false, false, false, false, false};
+    cudaEvent_t ev_chunk[2] = {};      // chunked fused build: upload stream -> main stream hand-over (alternating)
     cudaEvent_t ev_terms[2] = {};      // span of the term kernels since the last reset
     bool terms_open = false;
     // deferred weight verdict (MGC_OPT_DEFER_WEIGHT_CHECK)
@@ -144,6 +147,9 @@ struct mgc_graph {
     bool caps_fresh = true;            // capacity arrays not written yet since create/reset (hold garbage)
     bool tr_fresh = true;              // same for tr[]
     bool state_init = false;
+    bool flow_started = false;         // push kernels have run since the last reset: cap[] holds residuals, not the terms
+    bool fuse_build = true;            // mgc_build_voxel_graph uses the single-pass k_build_tile (MEDPY_GC_FUSE=0: four passes)
+    int build_chunks = 8;              // host inputs: z-chunks whose upload overlaps the build of the previous chunk
     bool solved = false;
     bool has_nlinks = false;
     double energy = 0.0;
@@ -173,6 +179,12 @@ struct mgc_graph {
     int tile_iters_first = 4;          // ... in the first round after init (mostly stranded excess: measured best at 512^3)
     int iters_now = 8;
     int passes0 = 1, passes_max = 32;  // two-colour passes per round: starts at passes0, at most doubles per round
+    // directional line sweeps in front of the worklist BFS (gc_sweep.cuh): used when more than 1/sweep_frac of the
+    // tiles are waiting for labels (hard instances: the sink is far from most of the lattice)
+    bool use_sweeps = true;
+    int sweep_frac = 8;                // sweep when pending tiles > ntiles / sweep_frac
+    int sweep_rounds_max = 4;
+    int sweep_done_frac = 64;          // hand over to the worklist BFS when violating tiles <= ntiles / sweep_done_frac
 
     // tuning
     int sweeps_per_round = 32;
@@ -266,7 +278,7 @@ void slots_release(mgc_graph* g, unsigned mask)
 {
     // only the slots this call's kernels actually read: marking the others would make the NEXT call's upload wait for
     // this call's kernel although it targets a different buffer
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 5; ++i)
         if (mask & (1u << i)) { cudaEventRecord(g->ev_slot[i], g->stream); g->slot_used[i] = true; }
 }
 
@@ -391,21 +403,28 @@ int check_pending(mgc_graph* g)
 
 // rank-3 float64 tensor maps with an 8x8x8 box over the local lattice (x fastest); driver entry point resolved at run
 // time so the library does not link libcuda
-bool make_push_maps(mgc_graph* g)
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+tmap_encode_fn tensor_map_encoder()
 {
-    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static encode_fn encode = nullptr;
+    static tmap_encode_fn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
             cudaGetLastError();
-            return false;
+            return nullptr;
         }
-        encode = (encode_fn)fn;
+        encode = (tmap_encode_fn)fn;
     }
+    return encode;
+}
+
+bool make_push_maps(mgc_graph* g)
+{
+    tmap_encode_fn encode = tensor_map_encoder();
+    if (!encode) return false;
     const cuuint64_t X = (cuuint64_t)g->L.dim[2], Y = (cuuint64_t)g->L.dim[1], Z = (cuuint64_t)g->L.dim[0];
     if (X % 2) return false;                                   // global strides must be multiples of 16 B
     const cuuint64_t dims[3] = {X, Y, Z};
@@ -487,6 +506,10 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
     if (!rc) { rc = alloc_buf(g, nb, &p); g->S.rmask = (uint8_t*)p; }
     if (!rc) { rc = alloc_buf(g, nb, &p); g->mask_dev = (uint8_t*)p; }
     g->n_partials = nblocks(g);
+    if (g->nd == 3) {   // k_build_tile writes one partial per 8 x 8 x 32 block
+        const unsigned nbuild = (unsigned)((g->L.dim[0] + 7) / 8) * (unsigned)((g->L.dim[1] + 7) / 8) * (unsigned)((g->L.dim[2] + 31) / 32);
+        if (nbuild > g->n_partials) g->n_partials = nbuild;
+    }
     if (!rc) { rc = alloc_buf(g, (size_t)g->n_partials * sizeof(double), &p); g->partials = (double*)p; }
     if (!rc) { rc = alloc_buf(g, 3 * 1024 * sizeof(double), &p); g->minmax_buf = p; }
     if (!rc) { rc = alloc_buf(g, 64, &p); g->d_scalars = (double*)p; }
@@ -508,6 +531,10 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
         if (const char* e2 = getenv("MEDPY_GC_PASSES0")) if (atoi(e2) > 0) g->passes0 = atoi(e2);
         if (const char* e3 = getenv("MEDPY_GC_PASSES_MAX")) if (atoi(e3) > 0) g->passes_max = atoi(e3);
         if (const char* e4 = getenv("MEDPY_GC_COOP")) g->use_coop = atoi(e4) != 0;
+        if (const char* e7 = getenv("MEDPY_GC_SWEEP")) g->use_sweeps = atoi(e7) != 0;
+        if (const char* e8 = getenv("MEDPY_GC_SWEEP_FRAC")) if (atoi(e8) > 0) g->sweep_frac = atoi(e8);
+        if (const char* e9 = getenv("MEDPY_GC_SWEEP_ROUNDS")) if (atoi(e9) > 0) g->sweep_rounds_max = atoi(e9);
+        if (const char* e10 = getenv("MEDPY_GC_SWEEP_DONE_FRAC")) if (atoi(e10) > 0) g->sweep_done_frac = atoi(e10);
         {
             const char* e6 = getenv("MEDPY_GC_TMA");
             const size_t smem = 2 * TMA_STAGE_BYTES + 6 * TILE_VOX * sizeof(double) + 1024 * sizeof(int) + 64;
@@ -565,7 +592,10 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
     cudaStreamCreateWithFlags(&g->up_stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&g->ev_up, cudaEventDisableTiming);
     for (auto& ev : g->ev_slot) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for (auto& ev : g->ev_chunk) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto& ev : g->ev_terms) cudaEventCreate(&ev);
+    if (const char* f1 = getenv("MEDPY_GC_FUSE")) g->fuse_build = atoi(f1) != 0;
+    if (const char* f2 = getenv("MEDPY_GC_CHUNKS")) if (atoi(f2) > 0) g->build_chunks = atoi(f2);
     cudaEventCreateWithFlags(&g->ev_bad, cudaEventDisableTiming);
     for (auto& ev : g->ev_b) cudaEventCreate(&ev);
     if (cudaHostAlloc((void**)&g->h_bad, sizeof(int), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); g->h_bad = nullptr; }
@@ -616,6 +646,39 @@ int minmax_launch(mgc_graph* g, const E* img)
     k_minmax_partial<E><<<nb, 256, 0, g->stream>>>(img, g->L.n, pm, px, pa);
     k_minmax_final<E><<<1, 32, 0, g->stream>>>(pm, px, pa, nb, g->d_scalars + 2);
     g->st.kernel_launches += 2;
+    return MGC_OK;
+}
+
+// parameters of one of the eight boundary terms; the linear normaliser is computed on the device (K0) when `norm` is NaN
+int boundary_params(mgc_graph* g, int kind, int dtype, const void* img, double sigma, const double* spacing, double norm, BoundaryParams* out)
+{
+    BoundaryParams P{};
+    P.fn = kind & 3;
+    // boundary_maximum_division computes the difference variant (energy_voxel.py:347)
+    P.use_max = (kind >= 4 && kind != MGC_BOUNDARY_MAXIMUM_DIVISION) ? 1 : 0;
+    P.sigma = (P.fn == 1) ? pow(sigma, 2) : sigma;   // math.pow(sigma, 2), energy_voxel.py:231
+    P.inv_sigma2 = (P.fn == 1 && P.sigma != 0.0) ? 1.0 / P.sigma : 0.0;
+    P.inv_spacing_on = spacing ? 1.0 : 0.0;
+    for (int d = 0; d < 4; ++d) P.spacing[d] = 1.0;
+    if (spacing) for (int d = 0; d < g->user_ndim; ++d) P.spacing[d + g->shift] = spacing[d];
+    P.norm = norm;
+    if (P.fn == 0 && std::isnan(norm)) {
+        if (g->slab) FAIL(MGC_E_ARG, "z-slab handles need the global normaliser of the linear terms");
+        int rc = MGC_OK;
+        switch (dtype) {
+            case MGC_F32: rc = minmax_launch<float>(g, (const float*)img); break;
+            case MGC_F64: rc = minmax_launch<double>(g, (const double*)img); break;
+            case MGC_U8: rc = minmax_launch<uint8_t>(g, (const uint8_t*)img); break;
+            case MGC_I16: rc = minmax_launch<int16_t>(g, (const int16_t*)img); break;
+            case MGC_I32: rc = minmax_launch<int32_t>(g, (const int32_t*)img); break;
+        }
+        if (rc) return rc;
+        double mm[2];
+        CK(cudaMemcpyAsync(mm, g->d_scalars + 2, sizeof(mm), cudaMemcpyDeviceToHost, g->stream));
+        CK(cudaStreamSynchronize(g->stream));
+        P.norm = (kind == MGC_BOUNDARY_MAXIMUM_LINEAR) ? mm[1] : mm[0];
+    }
+    *out = P;
     return MGC_OK;
 }
 
@@ -695,6 +758,7 @@ int count_active(mgc_graph* g, int64_t* out)
 // n push sweeps; *work_last = whether the last sweep still found an active voxel
 int push_sweeps(mgc_graph* g, int n, int* work_last)
 {
+    g->flow_started = true;
     if (work_last) cudaEventRecord(g->ev[2], g->stream);
     for (int i = 0; i < n; ++i) {
         if (i == n - 1) CK(cudaMemsetAsync(g->d_flags + 2, 0, sizeof(int), g->stream));
@@ -777,9 +841,54 @@ int relabel_tiles_begin(mgc_graph* g)
 }
 
 // run passes until the current worklist is empty; *any = 1 if any tile was visited
+// one round of directional sweeps (both directions of every axis), then the list of tiles that are not at the fixed
+// point yet (gc_sweep.cuh); *pending = number of such tiles (host synchronisation)
+int relabel_sweep_round(mgc_graph* g, int* pending)
+{
+    for (int a = 0; a < 2; ++a) {
+        if (g->L.dim[a] < 2) continue;
+        const unsigned nlines = g->L.n / (unsigned)g->L.dim[a];
+        k_sweep_axis<<<(nlines + 255u) / 256u, 256, 0, g->stream>>>(g->L, g->S.rmask, g->S.height, a);
+        g->st.kernel_launches++;
+    }
+    if (g->L.dim[2] >= 2) {
+        const unsigned nrows = g->L.n / (unsigned)g->L.dim[2];
+        unsigned grid = (nrows + SWEEP_WARPS - 1) / SWEEP_WARPS;
+        const unsigned cap = (unsigned)cached_sm_count(g->device) * 16u;
+        if (grid > cap) grid = cap;
+        k_sweep_rows<<<grid, 32 * SWEEP_WARPS, 0, g->stream>>>(g->L, g->S.rmask, g->S.height);
+        g->st.kernel_launches++;
+    }
+    CK(cudaMemsetAsync(g->d_tcount, 0, 2 * sizeof(int), g->stream));
+    CK(cudaMemsetAsync(g->rflag, 0, (size_t)g->TL.ntiles * sizeof(int), g->stream));
+    k_relabel_check<<<nblocks(g), 256, 0, g->stream>>>(g->L, g->TL, g->S.rmask, g->S.height, g->rflag, rl(g, 0));
+    g->st.kernel_launches++;
+    g->rl_cur = 0;
+    CK(cudaMemsetAsync(g->d_tcount + CTL_RLCUR, 0, sizeof(int), g->stream));
+    CK(cudaGetLastError());
+    g->st.relabel_sweeps++;
+    return read_tcount(g, 0, pending);
+}
+
 int relabel_tiles_run(mgc_graph* g, int* any, bool want_any = true)
 {
     *any = 0;
+    if (g->use_sweeps && g->nd == 3 && g->TL.ntiles >= 64) {
+        int pending = 0;
+        int rc = read_tcount(g, g->rl_cur, &pending);
+        if (rc) return rc;
+        if (pending > g->TL.ntiles / g->sweep_frac) {
+            *any = 1;
+            int prev = g->TL.ntiles + 1;
+            for (int r = 0; r < g->sweep_rounds_max; ++r) {
+                rc = relabel_sweep_round(g, &pending);
+                if (rc) return rc;
+                if (pending <= g->TL.ntiles / g->sweep_done_frac) break;
+                if ((long long)pending * 4 > (long long)prev * 3) break;      // a round that clears < 25 %: the rest is local detail
+                prev = pending;
+            }
+        }
+    }
     if (g->coop_bfs_grid > 0 && g->nd == 3) {
         // all passes in one cooperative launch; the list selector lives in the control block (device side), so the
         // host does not have to synchronise unless the caller wants to know whether anything moved
@@ -793,7 +902,7 @@ int relabel_tiles_run(mgc_graph* g, int* any, bool want_any = true)
             int relp = 0;
             CK(cudaMemcpyAsync(&relp, g->d_tcount + CTL_RELP, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
             CK(cudaStreamSynchronize(g->stream));
-            *any = relp != 0;
+            if (relp != 0) *any = 1;
         }
         return MGC_OK;
     }
@@ -840,6 +949,7 @@ int relabel_tiles(mgc_graph* g)
 // to the list the other colour consumes next
 int push_color(mgc_graph* g, int color)
 {
+    g->flow_started = true;
     const int a = g->pl_sel[color], oa = g->pl_sel[1 - color];
     CK(cudaMemsetAsync(cursor(g), 0, sizeof(int), g->stream));
     if (g->nd == 4) {
@@ -900,6 +1010,7 @@ int count_active_tiles(mgc_graph* g, int64_t* out)
 // selectors and the statistics are refreshed from the control block afterwards.
 int solve_coop(mgc_graph* g, int flags, int passes, int64_t* active_out)
 {
+    if (flags & (SOLVE_F_PUSH | SOLVE_F_LOOP)) g->flow_started = true;
     int hdr[4] = {0, g->pl_sel[0], g->pl_sel[1], g->rl_cur};     // cursor, list selectors
     CK(cudaMemcpyAsync(g->d_tcount + CTL_CURSOR, hdr, sizeof(hdr), cudaMemcpyHostToDevice, g->stream));
     SolveLists SL;
@@ -970,7 +1081,8 @@ int solve_tiles(mgc_graph* g)
 
 int readout(mgc_graph* g, double* energy_part)
 {
-    k_readout<double><<<rblocks(g), 256, 0, g->stream>>>(g->L, g->S, g->mask_dev, g->partials);
+    if (g->use_tiles && g->nd == 3) k_readout<double, true><<<rblocks(g), 256, 0, g->stream>>>(g->L, g->S, g->mask_dev, g->partials);
+    else                            k_readout<double, false><<<rblocks(g), 256, 0, g->stream>>>(g->L, g->S, g->mask_dev, g->partials);
     CK(cudaMemsetAsync(g->d_scalars + 1, 0, sizeof(double), g->stream));
     k_sum_partials<<<1, 256, 0, g->stream>>>(g->partials, rblocks(g), g->d_scalars + 1);
     g->st.kernel_launches += 2;
@@ -986,6 +1098,85 @@ int readout(mgc_graph* g, double* energy_part)
     }
     return MGC_OK;
 }
+
+// ---- fused graph build (gc_build.cuh) ------------------------------------------------------------------
+// rank-3 tensor map of the image with the 10 x 10 x BUILD_BX halo box; false when the 16-byte rules are not met
+bool make_image_map(mgc_graph* g, const void* img, int dtype, CUtensorMap* out)
+{
+    tmap_encode_fn encode = tensor_map_encoder();
+    if (!encode) return false;
+    const size_t es = dtype_size(dtype);
+    const cuuint64_t X = (cuuint64_t)g->L.dim[2], Y = (cuuint64_t)g->L.dim[1], Z = (cuuint64_t)g->L.dim[0];
+    if ((X * es) % 16 || ((uintptr_t)img & 15)) return false;
+    CUtensorMapDataType dt;
+    switch (dtype) {
+        case MGC_F32: dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; break;
+        case MGC_F64: dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT64; break;
+        case MGC_U8: dt = CU_TENSOR_MAP_DATA_TYPE_UINT8; break;
+        case MGC_I16: dt = CU_TENSOR_MAP_DATA_TYPE_UINT16; break;     // moved as raw 2-byte words
+        default: dt = CU_TENSOR_MAP_DATA_TYPE_INT32; break;
+    }
+    const cuuint64_t dims[3] = {X, Y, Z};
+    const cuuint64_t strides[2] = {X * es, X * Y * es};
+    const cuuint32_t box[3] = {BUILD_BX, BUILD_HY, BUILD_HZ};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return encode(out, dt, 3, const_cast<void*>(img), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename E, int FN, int USE_MAX, int SPACING>
+int build_launch_inst(mgc_graph* g, const CUtensorMap& imap, const BuildArgs& A, const BoundaryParams& P, int nz_layers)
+{
+    auto kern = k_build_tile<E, double, FN, USE_MAX, SPACING>;
+    const size_t smem = build_smem_bytes<E>();
+    static bool attr_done = false;       // per instantiation
+    if (!attr_done) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done = true; }
+    const dim3 grid((unsigned)((g->L.dim[2] + BUILD_TX - 1) / BUILD_TX), (unsigned)((g->L.dim[1] + BUILD_TY - 1) / BUILD_TY), (unsigned)nz_layers);
+    kern<<<grid, BUILD_THREADS, smem, g->stream>>>(g->L, g->TL, g->S, imap, A, P, g->d_flags, g->partials, g->rflag, rl(g, 0), g->pflag,
+                                                     pl(g, 0, 0), pl(g, 1, 0));
+    g->st.kernel_launches++;
+    CK(cudaGetLastError());
+    return MGC_OK;
+}
+
+template <typename E>
+int build_launch(mgc_graph* g, const CUtensorMap& imap, const BuildArgs& A, const BoundaryParams& P, int nz_layers)
+{
+    if constexpr (!std::is_integral<E>::value) {
+        if (P.fn == 1 && P.inv_spacing_on == 0.0) {
+            if (P.use_max) return build_launch_inst<E, 1, 1, 0>(g, imap, A, P, nz_layers);
+            return build_launch_inst<E, 1, 0, 0>(g, imap, A, P, nz_layers);
+        }
+    }
+    return build_launch_inst<E, -1, -1, -1>(g, imap, A, P, nz_layers);
+}
+
+int build_launch_dtype(mgc_graph* g, int dtype, const CUtensorMap& imap, const BuildArgs& A, const BoundaryParams& P, int nz_layers)
+{
+    switch (dtype) {
+        case MGC_F32: return build_launch<float>(g, imap, A, P, nz_layers);
+        case MGC_F64: return build_launch<double>(g, imap, A, P, nz_layers);
+        case MGC_U8: return build_launch<uint8_t>(g, imap, A, P, nz_layers);
+        case MGC_I16: return build_launch<int16_t>(g, imap, A, P, nz_layers);
+        default: return build_launch<int32_t>(g, imap, A, P, nz_layers);
+    }
+}
+
+// C-contiguous over the local lattice?
+bool c_contiguous(const mgc_graph* g, const mgc_array* a)
+{
+    long long expect = (long long)dtype_size(a->dtype);
+    for (int d = g->nd - 1; d >= 0; --d) {
+        const int ud = d - g->shift;
+        if (g->L.dim[d] > 1) {
+            if (ud < 0 || (long long)a->strides[ud] != expect) return false;
+        }
+        expect *= g->L.dim[d];
+    }
+    return true;
+}
+
+bool can_fuse(const mgc_graph* g) { return g->use_tiles && g->nd == 3 && g->fuse_build; }
 
 }  // namespace
 
@@ -1042,6 +1233,7 @@ void mgc_destroy(mgc_graph* g)
     for (auto& ev : g->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : g->ev_slot) if (ev) cudaEventDestroy(ev);
     for (auto& ev : g->ev_terms) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : g->ev_chunk) if (ev) cudaEventDestroy(ev);
     if (g->ev_up) cudaEventDestroy(g->ev_up);
     if (g->ev_bad) cudaEventDestroy(g->ev_bad);
     for (auto& ev : g->ev_b) if (ev) cudaEventDestroy(ev);
@@ -1061,6 +1253,7 @@ int mgc_reset(mgc_graph* g)
     CK(cudaMemsetAsync(g->d_scalars, 0, 64, g->stream));
     CK(cudaMemsetAsync(g->d_flags, 0, 64, g->stream));
     invalidate(g);
+    g->flow_started = false;
     g->has_nlinks = false;
     g->energy = 0.0;
     int64_t n = g->st.n_voxels;
@@ -1181,6 +1374,7 @@ int mgc_synchronize(mgc_graph* g)
 int mgc_add_regional_probability(mgc_graph* g, const mgc_array* prob, double alpha, int32_t compute_dtype)
 {
     if (!g || !prob) return MGC_E_ARG;
+    if (g->flow_started) FAIL(MGC_E_STATE, "the graph has been solved (its capacities hold residuals): reset() it before adding terms");
     if (prob->dtype != MGC_F32 && prob->dtype != MGC_F64) FAIL(MGC_E_ARG, "probability map must be float32 or float64");
     if (compute_dtype != MGC_F32 && compute_dtype != MGC_F64) FAIL(MGC_E_ARG, "compute dtype must be float32 or float64");
     CK(cudaSetDevice(g->device));
@@ -1209,6 +1403,7 @@ int mgc_add_regional_probability(mgc_graph* g, const mgc_array* prob, double alp
 int mgc_add_tweights_dense(mgc_graph* g, const mgc_array* src, const mgc_array* snk)
 {
     if (!g || !src || !snk) return MGC_E_ARG;
+    if (g->flow_started) FAIL(MGC_E_STATE, "the graph has been solved (its capacities hold residuals): reset() it before adding terms");
     if (src->dtype != MGC_F64 || snk->dtype != MGC_F64) FAIL(MGC_E_ARG, "dense t-weights must be float64");
     CK(cudaSetDevice(g->device));
     TermSpan t(g);
@@ -1234,13 +1429,14 @@ int mgc_add_markers(mgc_graph* g, const mgc_array* fg, const mgc_array* bg)
 {
     if (!g) return MGC_E_ARG;
     if (!fg && !bg) return MGC_OK;
+    if (g->flow_started) FAIL(MGC_E_STATE, "the graph has been solved (its capacities hold residuals): reset() it before adding terms");
     if ((fg && fg->dtype != MGC_U8) || (bg && bg->dtype != MGC_U8)) FAIL(MGC_E_ARG, "markers must be uint8 / bool");
     CK(cudaSetDevice(g->device));
     TermSpan t(g);
     const void *pf = nullptr, *pb = nullptr;
     int rc = MGC_OK;
-    if (fg) { rc = stage_input(g, fg, 0, &pf); if (rc) return rc; }
-    if (bg) { rc = stage_input(g, bg, 1, &pb); if (rc) return rc; }
+    if (fg) { rc = stage_input(g, fg, 1, &pf); if (rc) return rc; }
+    if (bg) { rc = stage_input(g, bg, 4, &pb); if (rc) return rc; }
     rc = check_pending(g);      // after the uploads: they overlapped the boundary kernel whose verdict this is
     if (rc) return rc;
     const bool vec16 = !g->tr_fresh && (g->L.n % 16u) == 0u && ((uintptr_t)pf % 16u) == 0u && ((uintptr_t)pb % 16u) == 0u;
@@ -1254,13 +1450,14 @@ int mgc_add_markers(mgc_graph* g, const mgc_array* fg, const mgc_array* bg)
     rc = finish_flow_const(g);
     if (rc) return rc;
     invalidate(g);
-    t.stop(3u);
+    t.stop(0x12u);
     return MGC_OK;
 }
 
 int mgc_add_boundary(mgc_graph* g, int32_t kind, const mgc_array* image, double sigma, const double* spacing, double norm)
 {
     if (!g || !image) return MGC_E_ARG;
+    if (g->flow_started) FAIL(MGC_E_STATE, "the graph has been solved (its capacities hold residuals): reset() it before adding terms");
     if (kind < 0 || kind > 7) FAIL(MGC_E_ARG, "unknown boundary term");
     CK(cudaSetDevice(g->device));
     { int rc0 = check_pending(g); if (rc0) return rc0; }
@@ -1269,30 +1466,8 @@ int mgc_add_boundary(mgc_graph* g, int32_t kind, const mgc_array* image, double 
     int rc = stage_input(g, image, 2, &img);
     if (rc) return rc;
     BoundaryParams P{};
-    P.fn = kind & 3;
-    // boundary_maximum_division computes the difference variant (energy_voxel.py:347)
-    P.use_max = (kind >= 4 && kind != MGC_BOUNDARY_MAXIMUM_DIVISION) ? 1 : 0;
-    P.sigma = (P.fn == 1) ? pow(sigma, 2) : sigma;   // math.pow(sigma, 2), energy_voxel.py:231
-    P.inv_sigma2 = (P.fn == 1 && P.sigma != 0.0) ? 1.0 / P.sigma : 0.0;
-    P.inv_spacing_on = spacing ? 1.0 : 0.0;
-    for (int d = 0; d < 4; ++d) P.spacing[d] = 1.0;
-    if (spacing) for (int d = 0; d < g->user_ndim; ++d) P.spacing[d + g->shift] = spacing[d];
-    P.norm = norm;
-    if (P.fn == 0 && std::isnan(norm)) {
-        if (g->slab) FAIL(MGC_E_ARG, "z-slab handles need the global normaliser of the linear terms");
-        switch (image->dtype) {
-            case MGC_F32: rc = minmax_launch<float>(g, (const float*)img); break;
-            case MGC_F64: rc = minmax_launch<double>(g, (const double*)img); break;
-            case MGC_U8: rc = minmax_launch<uint8_t>(g, (const uint8_t*)img); break;
-            case MGC_I16: rc = minmax_launch<int16_t>(g, (const int16_t*)img); break;
-            case MGC_I32: rc = minmax_launch<int32_t>(g, (const int32_t*)img); break;
-        }
-        if (rc) return rc;
-        double mm[2];
-        CK(cudaMemcpyAsync(mm, g->d_scalars + 2, sizeof(mm), cudaMemcpyDeviceToHost, g->stream));
-        CK(cudaStreamSynchronize(g->stream));
-        P.norm = (kind == MGC_BOUNDARY_MAXIMUM_LINEAR) ? mm[1] : mm[0];
-    }
+    rc = boundary_params(g, kind, image->dtype, img, sigma, spacing, norm, &P);
+    if (rc) return rc;
     CK(cudaMemsetAsync(g->d_flags, 0, sizeof(int), g->stream));
     cudaEventRecord(g->ev_b[0], g->stream);
     switch (image->dtype) {
@@ -1323,9 +1498,178 @@ int mgc_add_boundary(mgc_graph* g, int32_t kind, const mgc_array* image, double 
     return MGC_OK;
 }
 
+int mgc_can_fuse(const mgc_graph* g) { return g && can_fuse(g) ? 1 : 0; }
+
+int mgc_build_voxel_graph(mgc_graph* g, const mgc_voxel_terms* t)
+{
+    if (!g || !t) return MGC_E_ARG;
+    if (g->flow_started) FAIL(MGC_E_STATE, "the graph has been solved (its capacities hold residuals): reset() it before adding terms");
+    const bool has_bits = t->fg_bits || t->bg_bits;
+    if (has_bits && (t->fg || t->bg)) FAIL(MGC_E_ARG, "pass the markers either as byte arrays or bit-packed, not both");
+    if (t->boundary_kind > 7) FAIL(MGC_E_ARG, "unknown boundary term");
+    if (t->boundary_kind >= 0 && !t->image) FAIL(MGC_E_ARG, "boundary term without image");
+    const bool fresh = g->caps_fresh && g->tr_fresh && !g->state_init;
+    if (!(fresh && can_fuse(g) && t->boundary_kind >= 0)) {
+        // the same terms through the one-pass-per-term entry points, in the reference's order (generate.py:159-172)
+        if (has_bits) FAIL(MGC_E_ARG, "bit-packed markers need the fused build (fresh 1-D..3-D tile-solver handle with a boundary term)");
+        int rc = MGC_OK;
+        if (t->prob) { rc = mgc_add_regional_probability(g, t->prob, t->alpha, t->compute_dtype); if (rc) return rc; }
+        if (t->boundary_kind >= 0) { rc = mgc_add_boundary(g, t->boundary_kind, t->image, t->sigma, t->spacing, t->norm); if (rc) return rc; }
+        return mgc_add_markers(g, t->fg, t->bg);
+    }
+    if (t->prob && t->prob->dtype != MGC_F32 && t->prob->dtype != MGC_F64) FAIL(MGC_E_ARG, "probability map must be float32 or float64");
+    if (t->prob && t->compute_dtype != MGC_F32 && t->compute_dtype != MGC_F64) FAIL(MGC_E_ARG, "compute dtype must be float32 or float64");
+    if (t->prob && t->compute_dtype == MGC_F32 && t->prob->dtype != MGC_F32) FAIL(MGC_E_ARG, "float32 products need a float32 probability map");
+    if ((t->fg && t->fg->dtype != MGC_U8) || (t->bg && t->bg->dtype != MGC_U8)) FAIL(MGC_E_ARG, "markers must be uint8 / bool");
+    if (!dtype_size(t->image->dtype)) FAIL(MGC_E_ARG, "unsupported dtype");
+    CK(cudaSetDevice(g->device));
+    { int rc0 = check_pending(g); if (rc0) return rc0; }
+    TermSpan span(g);
+
+    const size_t n = (size_t)g->L.n;
+    const size_t plane = (size_t)g->L.plane;
+    const int Z = g->L.dim[0];
+    const int nzt = (Z + BUILD_TZ - 1) / BUILD_TZ;
+    const size_t es_img = dtype_size(t->image->dtype), es_prob = t->prob ? dtype_size(t->prob->dtype) : 0;
+    const size_t words = (n + 31) / 32;
+
+    // ---- chunked path: contiguous HOST arrays, upload of z-chunk c+1 overlaps the build of chunk c ----
+    bool chunked = g->build_chunks > 1 && nzt >= 2 && t->image->mem == MGC_MEM_HOST && c_contiguous(g, t->image) &&
+                   !(( t->boundary_kind & 3) == 0 && std::isnan(t->norm));
+    if (t->prob) chunked = chunked && t->prob->mem == MGC_MEM_HOST && c_contiguous(g, t->prob);
+    if (t->fg) chunked = chunked && t->fg->mem == MGC_MEM_HOST && c_contiguous(g, t->fg);
+    if (t->bg) chunked = chunked && t->bg->mem == MGC_MEM_HOST && c_contiguous(g, t->bg);
+    if (has_bits) chunked = chunked && t->bits_mem == MGC_MEM_HOST;
+
+    const void *d_img = nullptr, *d_prob = nullptr, *d_fg = nullptr, *d_bg = nullptr;
+    int rc = MGC_OK;
+    if (!chunked) {
+        rc = stage_input(g, t->image, 2, &d_img); if (rc) return rc;
+        if (t->prob) { rc = stage_input(g, t->prob, 0, &d_prob); if (rc) return rc; }
+        if (t->fg) { rc = stage_input(g, t->fg, 1, &d_fg); if (rc) return rc; }
+        if (t->bg) { rc = stage_input(g, t->bg, 4, &d_bg); if (rc) return rc; }
+        if (has_bits) {
+            const uint32_t* src[2] = {t->fg_bits, t->bg_bits};
+            const void** dst[2] = {&d_fg, &d_bg};
+            const int slot[2] = {1, 4};
+            for (int i = 0; i < 2; ++i) {
+                if (!src[i]) continue;
+                if (t->bits_mem == MGC_MEM_DEVICE) { *dst[i] = src[i]; continue; }
+                rc = ensure_scratch(g, g->scratch[slot[i]], words * 4); if (rc) return rc;
+                rc = upload(g, g->scratch[slot[i]].p, src[i], words * 4, slot[i]); if (rc) return rc;
+                *dst[i] = g->scratch[slot[i]].p;
+            }
+        }
+    } else {
+        rc = ensure_scratch(g, g->scratch[2], n * es_img); if (rc) return rc;
+        if (t->prob) { rc = ensure_scratch(g, g->scratch[0], n * es_prob); if (rc) return rc; }
+        if (t->fg || t->fg_bits) { rc = ensure_scratch(g, g->scratch[1], has_bits ? words * 4 : n); if (rc) return rc; }
+        if (t->bg || t->bg_bits) { rc = ensure_scratch(g, g->scratch[4], has_bits ? words * 4 : n); if (rc) return rc; }
+        d_img = g->scratch[2].p;
+        if (t->prob) d_prob = g->scratch[0].p;
+        if (t->fg || t->fg_bits) d_fg = g->scratch[1].p;
+        if (t->bg || t->bg_bits) d_bg = g->scratch[4].p;
+        const int slots[4] = {0, 1, 2, 4};
+        for (int i = 0; i < 4; ++i) if (g->slot_used[slots[i]]) CK(cudaStreamWaitEvent(g->up_stream, g->ev_slot[slots[i]], 0));
+    }
+
+    BoundaryParams P{};
+    rc = boundary_params(g, t->boundary_kind, t->image->dtype, d_img, t->sigma, t->spacing, t->norm, &P);
+    if (rc) return rc;
+
+    BuildArgs A{};
+    A.img = d_img;
+    A.prob = d_prob;
+    A.prob_f64 = (t->prob && t->prob->dtype == MGC_F64) ? 1 : 0;
+    A.compute_f32 = (t->prob && t->compute_dtype == MGC_F32) ? 1 : 0;
+    A.alpha = t->alpha;
+    if (has_bits) { A.fg_bits = (const unsigned*)d_fg; A.bg_bits = (const unsigned*)d_bg; }
+    else { A.fg = (const uint8_t*)d_fg; A.bg = (const uint8_t*)d_bg; }
+    CUtensorMap imap{};
+    A.use_tma = make_image_map(g, d_img, t->image->dtype, &imap) ? 1 : 0;
+    if (const char* e = getenv("MEDPY_GC_BUILD_TMA")) if (atoi(e) == 0) A.use_tma = 0;
+
+    CK(cudaMemsetAsync(g->d_tcount, 0, 256, g->stream));
+    CK(cudaMemsetAsync(g->d_flags, 0, sizeof(int), g->stream));
+    g->pl_sel[0] = g->pl_sel[1] = 0;
+    cudaEventRecord(g->ev_b[0], g->stream);
+    if (!chunked) {
+        A.z_tile0 = 0;
+        rc = build_launch_dtype(g, t->image->dtype, imap, A, P, nzt);
+        if (rc) return rc;
+    } else {
+        int nchunks = g->build_chunks < nzt ? g->build_chunks : nzt;
+        const int per = (nzt + nchunks - 1) / nchunks;
+        nchunks = (nzt + per - 1) / per;
+        const char* h_img = (const char*)t->image->data;
+        int prev_l0 = 0, prev_nl = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            const int l0 = c * per, l1 = (l0 + per < nzt) ? l0 + per : nzt;
+            const size_t z0 = (size_t)l0 * BUILD_TZ, z1 = ((size_t)l1 * BUILD_TZ < (size_t)Z) ? (size_t)l1 * BUILD_TZ : (size_t)Z;
+            const size_t v0 = z0 * plane, nv = (z1 - z0) * plane;
+            CK(cudaMemcpyAsync((char*)g->scratch[2].p + v0 * es_img, h_img + v0 * es_img, nv * es_img, cudaMemcpyHostToDevice, g->up_stream));
+            if (c > 0) {
+                // chunk c-1 needs the first image plane of chunk c (its +z neighbours) and its own prob / markers
+                CK(cudaEventRecord(g->ev_chunk[c & 1], g->up_stream));
+                CK(cudaStreamWaitEvent(g->stream, g->ev_chunk[c & 1], 0));
+                A.z_tile0 = prev_l0;
+                rc = build_launch_dtype(g, t->image->dtype, imap, A, P, prev_nl);
+                if (rc) return rc;
+            }
+            if (t->prob) CK(cudaMemcpyAsync((char*)g->scratch[0].p + v0 * es_prob, (const char*)t->prob->data + v0 * es_prob, nv * es_prob, cudaMemcpyHostToDevice, g->up_stream));
+            if (has_bits) {
+                const size_t w0 = v0 / 32, w1 = (v0 + nv + 31) / 32;
+                if (t->fg_bits) CK(cudaMemcpyAsync((uint32_t*)g->scratch[1].p + w0, t->fg_bits + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, g->up_stream));
+                if (t->bg_bits) CK(cudaMemcpyAsync((uint32_t*)g->scratch[4].p + w0, t->bg_bits + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, g->up_stream));
+            } else {
+                if (t->fg) CK(cudaMemcpyAsync((char*)g->scratch[1].p + v0, (const char*)t->fg->data + v0, nv, cudaMemcpyHostToDevice, g->up_stream));
+                if (t->bg) CK(cudaMemcpyAsync((char*)g->scratch[4].p + v0, (const char*)t->bg->data + v0, nv, cudaMemcpyHostToDevice, g->up_stream));
+            }
+            prev_l0 = l0; prev_nl = l1 - l0;
+        }
+        CK(cudaEventRecord(g->ev_up, g->up_stream));
+        CK(cudaStreamWaitEvent(g->stream, g->ev_up, 0));
+        A.z_tile0 = prev_l0;
+        rc = build_launch_dtype(g, t->image->dtype, imap, A, P, prev_nl);
+        if (rc) return rc;
+        CK(cudaEventSynchronize(g->ev_up));       // the host arrays are only borrowed for this call
+    }
+    cudaEventRecord(g->ev_b[1], g->stream);
+    {   // flow constant: one partial per build block, fixed order
+        const unsigned nbuild = (unsigned)nzt * (unsigned)((g->L.dim[1] + BUILD_TY - 1) / BUILD_TY) * (unsigned)((g->L.dim[2] + BUILD_TX - 1) / BUILD_TX);
+        k_sum_partials<<<1, 256, 0, g->stream>>>(g->partials, nbuild, g->d_scalars);
+        g->st.kernel_launches++;
+        CK(cudaGetLastError());
+    }
+    g->caps_fresh = false;
+    g->tr_fresh = false;
+    g->has_nlinks = true;
+    g->boundary_timed = true;
+    g->state_init = true;
+    g->solved = false;
+    g->host_mask_valid = false;
+    g->labels_fresh = true;
+    g->rl_cur = 0;
+    g->init_timed = false;
+    g->st.ms_init = 0.0;
+    span.stop(0x17u);
+    if (g->defer_check && g->h_bad) {
+        CK(cudaMemcpyAsync(g->h_bad, g->d_flags, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+        CK(cudaEventRecord(g->ev_bad, g->stream));
+        g->bad_pending = true;
+        return MGC_OK;
+    }
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, g->d_flags, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    if (bad) FAIL(MGC_E_WEIGHT, "Negative or zero weights are not allowed.");
+    return MGC_OK;
+}
+
 int mgc_add_nweights_dense(mgc_graph* g, int32_t axis, const mgc_array* fwd, const mgc_array* bwd)
 {
     if (!g || !fwd || !bwd) return MGC_E_ARG;
+    if (g->flow_started) FAIL(MGC_E_STATE, "the graph has been solved (its capacities hold residuals): reset() it before adding terms");
     if (axis < 0 || axis >= g->user_ndim) FAIL(MGC_E_ARG, "bad axis");
     if (fwd->dtype != MGC_F64 || bwd->dtype != MGC_F64) FAIL(MGC_E_ARG, "dense n-weights must be float64");
     CK(cudaSetDevice(g->device));
@@ -1478,9 +1822,12 @@ int mgc_get_trcap(mgc_graph* g, int64_t node, double* trcap)
         return MGC_OK;
     }
     double e = 0, s = 0;
+    uint8_t rm = 0x80u;
     CK(cudaMemcpyAsync(&e, g->S.excess + node, sizeof(double), cudaMemcpyDeviceToHost, g->stream));
     CK(cudaMemcpyAsync(&s, g->S.sink + node, sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+    if (g->use_tiles && g->nd == 3) CK(cudaMemcpyAsync(&rm, g->S.rmask + node, 1, cudaMemcpyDeviceToHost, g->stream));
     CK(cudaStreamSynchronize(g->stream));
+    if (!(rm & 0x80u)) s = 0;        // RM_SINKV clear: nothing absorbed yet, the entry was never written
     double tr = 0;
     CK(cudaMemcpyAsync(&tr, g->S.tr + node, sizeof(double), cudaMemcpyDeviceToHost, g->stream));
     CK(cudaStreamSynchronize(g->stream));

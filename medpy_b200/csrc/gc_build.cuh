@@ -1,0 +1,279 @@
+// gc_build.cuh -- the whole graph build as ONE pass over the lattice (3-D): n-link stencil + regional t-links + hard
+// markers + solver-state initialisation, fused.
+//
+// Replaces, in one kernel, what the reference does in  energy_voxel.py:611-664 (__skeleton_base, one Python call
+// per edge), graph.py:532-552 / :310-380 (set_tweights_all, set_source_nodes, set_sink_nodes -> Graph::add_tweights,
+// graph.h:415-425) in the order graph_from_voxels applies them (generate.py:159-172: regional term, boundary term,
+// foreground markers, background markers), plus what k_boundary / k_regional / k_markers / k_init_tile did in four
+// passes here (r01: 24.5 GB of DRAM traffic per 512^3 step, 6.4 GB of it capacity planes written by one kernel and
+// read straight back by the next).  Now every input byte is read once and every state byte written once:
+//     read  image 4 + probability 4 + fg 1 + bg 1                         = 10 B/voxel (float32 inputs)
+//     write six float64 capacities 48 + tr 8 + excess 8 + label 4 + rmask 1 = 69 B/voxel
+// (`sink[]`, the absorbed-flow accumulator, is no longer zero-filled: bit RM_SINKV of rmask says whether a voxel's
+// entry has been written, see gc_tiles.cuh.)
+//
+// Geometry: a 256-thread CTA builds an 8 (z) x 8 (y) x 32 (x) block = four 8^3 solver tiles in a row.  The image
+// block with a one-voxel halo on every side (10 x 10 x 34, box 10 x 10 x BUILD_BX) is staged in shared memory by ONE
+// `cp.async.bulk.tensor.3d` box copy against a per-call tensor map (SASS: UTMALDG + SYNCS; out-of-lattice parts are
+// zero-filled by the TMA unit and masked by coordinates), or by plain loads when the image does not meet the 16-byte
+// stride rule of tensor maps.  Thread (y, x) marches through z = -1 .. 7: per step it evaluates the three FORWARD
+// pair weights of its voxel (+z, +y, +x) exactly once -- w(p, q) = g(|I_p - I_q|) or g(max(|I_p|, |I_q|)), float64,
+// the arithmetic of gc_terms.cuh -- keeps the +z weight in a register for the next step (where it is the voxel's -z
+// capacity), and publishes the +y / +x weights in a shared-memory plane from which the neighbours in y and x take
+// their backward capacities.  The only weights evaluated twice are those on the block's low faces (12.5 %).
+#pragma once
+#include "gc_terms.cuh"
+#include "gc_tiles.cuh"
+#include "gc_tma.cuh"
+
+#define BUILD_TZ 8
+#define BUILD_TY 8
+#define BUILD_TX 32
+#define BUILD_THREADS 256
+#define BUILD_BX 48            // inner box extent: >= 34 and a multiple of 16 bytes for every element size
+#define BUILD_HY 10
+#define BUILD_HZ 10
+
+struct BuildArgs {
+    const void* img;           // C-contiguous image over the local lattice (device)
+    const void* prob;          // regional_probability_map input or nullptr
+    int prob_f64;              // 1: prob is float64
+    int compute_f32;           // products in float32 (numpy: float32 map * Python float)
+    double alpha;
+    const uint8_t* fg;         // marker volumes (bytes) or nullptr
+    const uint8_t* bg;
+    const unsigned* fg_bits;   // ... or bit-packed (bit v & 31 of word v >> 5), used when fg/bg are nullptr
+    const unsigned* bg_bits;
+    int use_tma;               // image block staged by TMA (else plain loads)
+    int z_tile0;               // first z tile layer of this launch (chunked builds)
+};
+
+template <typename E>
+__device__ __forceinline__ double build_val(E x, bool use_max)
+{
+    return use_max ? Elem<E>::val(Elem<E>::absv(x)) : Elem<E>::val(x);
+}
+
+template <int FN, typename E>
+__device__ __forceinline__ double build_pair(const BoundaryParams& P, double a, E iq, bool use_max)
+{
+    const double b = build_val<E>(iq, use_max);
+    const double x = use_max ? fmax(a, b) : fabs(__dsub_rn(a, b));
+    return g_weight<FN>(P, x);
+}
+
+template <typename E, typename T, int FN, int USE_MAX, int SPACING>
+__global__ void __launch_bounds__(BUILD_THREADS)
+k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMap imap, BuildArgs A, BoundaryParams P,
+             int* __restrict__ bad, double* __restrict__ partials, int* __restrict__ rflag, WorkList rl,
+             int* __restrict__ pflag, WorkList pl0, WorkList pl1)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    E* s_img = reinterpret_cast<E*>(smem_raw);                                   // [10][10][BUILD_BX]
+    constexpr int IMG_BYTES = BUILD_HZ * BUILD_HY * BUILD_BX * (int)sizeof(E);
+    constexpr int IMG_PAD = (IMG_BYTES + 127) / 128 * 128;
+    double* s_wy = reinterpret_cast<double*>(smem_raw + IMG_PAD);                // [2][9][32]: +y weight of row y-1 .. 7
+    double* s_wx = s_wy + 2 * 9 * 32;                                            // [2][8][33]: +x weight of column x-1 .. 31
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(s_wx + 2 * 8 * 33);
+    int* s_flags = reinterpret_cast<int*>(bar + 1);                              // [4] needs, [4] has excess
+    double* s_red = reinterpret_cast<double*>(s_flags + 8);                      // [8] block reduction
+
+    const int tid = threadIdx.x;
+    const int lx = tid & 31, ly = tid >> 5;
+    const int x0 = blockIdx.x * BUILD_TX, y0 = blockIdx.y * BUILD_TY, z0 = (A.z_tile0 + (int)blockIdx.z) * BUILD_TZ;
+    const bool use_max = USE_MAX >= 0 ? (USE_MAX != 0) : (P.use_max != 0);
+    const bool spacing = SPACING >= 0 ? (SPACING != 0) : (P.inv_spacing_on != 0.0);
+
+    // ---- stage the image block with halo: local (hz, hy, hx) <-> global (z0 - 1 + hz, y0 - 1 + hy, x0 - 1 + hx) ----
+    if (tid < 8) s_flags[tid] = 0;
+    if (A.use_tma) {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(bar, (unsigned)IMG_BYTES);
+            tma_load_3d(s_img, &imap, bar, x0 - 1, y0 - 1, z0 - 1);
+        }
+        __syncthreads();
+        mbar_wait(bar, 0u);
+    } else {
+        const E* img = reinterpret_cast<const E*>(A.img);
+        for (int i = tid; i < BUILD_HZ * BUILD_HY * 34; i += BUILD_THREADS) {
+            const int hx = i % 34, r = i / 34, hy = r % BUILD_HY, hz = r / BUILD_HY;
+            const int gz = z0 - 1 + hz, gy = y0 - 1 + hy, gx = x0 - 1 + hx;
+            E val = (E)0;
+            if (gz >= 0 && gy >= 0 && gx >= 0 && gz < L.dim[0] && gy < L.dim[1] && gx < L.dim[2])
+                val = img[(unsigned)gz * L.stride[0] + (unsigned)gy * L.stride[1] + (unsigned)gx];
+            s_img[(hz * BUILD_HY + hy) * BUILD_BX + hx] = val;
+        }
+        __syncthreads();
+    }
+
+    const int gy = y0 + ly, gx = x0 + lx;
+    const bool col_in = gy < L.dim[1] && gx < L.dim[2];
+    const bool has_py = gy + 1 < L.dim[1], has_px = gx + 1 < L.dim[2];
+    const double inv_sp_z = spacing ? P.spacing[0] : 1.0, inv_sp_y = spacing ? P.spacing[1] : 1.0, inv_sp_x = spacing ? P.spacing[2] : 1.0;
+    auto at = [&](int hz, int hy, int hx) -> E { return s_img[(hz * BUILD_HY + hy) * BUILD_BX + hx]; };
+
+    int isbad = 0;
+    unsigned needs_any = 0, exc_any = 0;
+    double msum = 0.0;
+    // -z capacity of the first plane: pair (z0 - 1, z0)
+    double wz_back = 0.0;
+    if (col_in && z0 > 0 && z0 < L.dim[0]) {
+        const double a = build_val<E>(at(0, ly + 1, lx + 1), use_max);
+        double w = build_pair<FN, E>(P, a, at(1, ly + 1, lx + 1), use_max);
+        if (spacing) w = __ddiv_rn(w, inv_sp_z);
+        if (w <= 0.0) isbad = 1;
+        wz_back = w;
+    }
+
+    for (int lz = 0; lz < BUILD_TZ; ++lz) {
+        const int gz = z0 + lz;
+        const bool pin = col_in && gz < L.dim[0];            // block-uniform in z, per thread in y/x
+        double* wyb = s_wy + (lz & 1) * 9 * 32;
+        double* wxb = s_wx + (lz & 1) * 8 * 33;
+        const int hz = lz + 1;
+        double wz = 0.0, wy = 0.0, wx = 0.0;
+        if (gz < L.dim[0]) {
+            if (pin) {
+                const double a = build_val<E>(at(hz, ly + 1, lx + 1), use_max);
+                if (gz + 1 < L.dim[0]) { wz = build_pair<FN, E>(P, a, at(hz + 1, ly + 1, lx + 1), use_max); if (spacing) wz = __ddiv_rn(wz, inv_sp_z); if (wz <= 0.0) isbad = 1; }
+                if (has_py) { wy = build_pair<FN, E>(P, a, at(hz, ly + 2, lx + 1), use_max); if (spacing) wy = __ddiv_rn(wy, inv_sp_y); if (wy <= 0.0) isbad = 1; }
+                if (has_px) { wx = build_pair<FN, E>(P, a, at(hz, ly + 1, lx + 2), use_max); if (spacing) wx = __ddiv_rn(wx, inv_sp_x); if (wx <= 0.0) isbad = 1; }
+            }
+            wyb[(ly + 1) * 32 + lx] = wy;
+            wxb[ly * 33 + lx + 1] = wx;
+            // low faces of the block: pair (y0 - 1, y0) by warp 0, pair (x0 - 1, x0) by the first 8 lanes of warp 1
+            if (ly == 0) {
+                double w = 0.0;
+                if (y0 > 0 && gx < L.dim[2]) {
+                    const double a = build_val<E>(at(hz, 0, lx + 1), use_max);
+                    w = build_pair<FN, E>(P, a, at(hz, 1, lx + 1), use_max);
+                    if (spacing) w = __ddiv_rn(w, inv_sp_y);
+                    if (w <= 0.0) isbad = 1;
+                }
+                wyb[lx] = w;
+            } else if (ly == 1 && lx < 8) {
+                double w = 0.0;
+                if (x0 > 0 && y0 + lx < L.dim[1]) {
+                    const double a = build_val<E>(at(hz, lx + 1, 0), use_max);
+                    w = build_pair<FN, E>(P, a, at(hz, lx + 1, 1), use_max);
+                    if (spacing) w = __ddiv_rn(w, inv_sp_x);
+                    if (w <= 0.0) isbad = 1;
+                }
+                wxb[lx * 33] = w;
+            }
+        }
+        __syncthreads();
+        if (pin) {
+            const unsigned v = (unsigned)gz * L.stride[0] + (unsigned)gy * L.stride[1] + (unsigned)gx;
+            const double c0 = wz_back, c1 = wz, c2 = wyb[ly * 32 + lx], c3 = wy, c4 = wxb[ly * 33 + lx], c5 = wx;
+            S.cap[0][v] = (T)c0; S.cap[1][v] = (T)c1; S.cap[2][v] = (T)c2;
+            S.cap[3][v] = (T)c3; S.cap[4][v] = (T)c4; S.cap[5][v] = (T)c5;
+            // ---- t-links: add_tweights replay in the reference's order (regional, fg, bg) ----
+            T tr = (T)0;
+            double mm = 0.0;
+            if (A.prob) {
+                double s, t;
+                if (A.compute_f32) {
+                    const float p = A.prob_f64 ? (float)reinterpret_cast<const double*>(A.prob)[v] : reinterpret_cast<const float*>(A.prob)[v];
+                    const float af = (float)A.alpha;
+                    s = (double)__fmul_rn(p, af);
+                    t = (double)__fmul_rn(__fsub_rn(1.0f, p), af);
+                } else {
+                    const double p = A.prob_f64 ? reinterpret_cast<const double*>(A.prob)[v] : (double)reinterpret_cast<const float*>(A.prob)[v];
+                    s = __dmul_rn(p, A.alpha);
+                    t = __dmul_rn(__dsub_rn(1.0, p), A.alpha);
+                }
+                mm = add_tweights_dev(tr, s, t);
+            }
+            bool f, b;
+            if (A.fg_bits || A.bg_bits) {
+                f = A.fg_bits && ((A.fg_bits[v >> 5] >> (v & 31u)) & 1u);
+                b = A.bg_bits && ((A.bg_bits[v >> 5] >> (v & 31u)) & 1u);
+            } else {
+                f = A.fg && A.fg[v];
+                b = A.bg && A.bg[v];
+            }
+            if (f) mm = __dadd_rn(mm, add_tweights_dev(tr, 65535.0, 0.0));
+            if (b) mm = __dadd_rn(mm, add_tweights_dev(tr, 0.0, 65535.0));
+            const bool own = gz >= L.own0 && gz < L.own1;
+            if (own) msum = __dadd_rn(msum, mm);
+            S.tr[v] = tr;
+            // ---- solver state (same arithmetic as k_init_tile) ----
+            unsigned m = (c0 > 0 ? 1u : 0u) | (c1 > 0 ? 2u : 0u) | (c2 > 0 ? 4u : 0u) | (c3 > 0 ? 8u : 0u) |
+                         (c4 > 0 ? 16u : 0u) | (c5 > 0 ? 32u : 0u);
+            double out = __dadd_ru(0.0, c0);
+            out = __dadd_ru(out, c1); out = __dadd_ru(out, c2); out = __dadd_ru(out, c3);
+            out = __dadd_ru(out, c4); out = __dadd_ru(out, c5);
+            const double trd = (double)tr;
+            double e = 0.0;
+            if (trd > 0) { const double lim = out * SOURCE_CLAMP_SLACK; e = trd < lim ? trd : lim; if (!(out == out)) e = trd; }
+            if (trd < 0) m |= RM_SINK;
+            if (!own) e = 0.0;
+            S.excess[v] = (T)e;
+            S.rmask[v] = (uint8_t)m;
+            const int h = (own && trd < 0) ? 1 : MGC_HINF;
+            S.height[v] = h;
+            if (own && (m & 0x3fu) != 0 && h == MGC_HINF) needs_any = 1u;
+            if (e > 0) exc_any = 1u;
+        }
+        wz_back = wz;
+        // the planes of this step are read above; the next step writes the other buffer, the one after waits at its barrier
+    }
+
+    // ---- per solver tile flags and worklists (a warp row covers four 8^3 tiles: lanes 8j .. 8j+7) ----
+    const unsigned bn = __ballot_sync(0xffffffffu, needs_any != 0), be = __ballot_sync(0xffffffffu, exc_any != 0);
+    if (lx == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if ((bn >> (8 * j)) & 0xffu) atomicOr(&s_flags[j], 1);
+            if ((be >> (8 * j)) & 0xffu) atomicOr(&s_flags[4 + j], 1);
+        }
+    }
+    if (isbad) *bad = 1;
+    // deterministic block sum of the add_tweights minima (fixed order: thread chain, warp shuffles, 8 warps)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) msum = __dadd_rn(msum, __shfl_down_sync(0xffffffffu, msum, o));
+    if (lx == 0) s_red[ly] = msum;
+    __syncthreads();
+    if (tid == 0) {
+        double t = s_red[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) t = __dadd_rn(t, s_red[w]);
+        partials[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = t;
+    }
+    if (tid < 4) {
+        const int tx = (x0 >> 3) + tid, ty = y0 >> 3, tz = z0 >> 3;
+        if (tx < TL.nt[2] && ty < TL.nt[1] && tz < TL.nt[0]) {
+            const int t = (tz * TL.nt[1] + ty) * TL.nt[2] + tx;
+            const int any_needs = s_flags[tid], any_exc = s_flags[4 + tid];
+            rflag[t] = any_needs;
+            if (any_needs) rl.items[atomicAdd(rl.count, 1)] = t;
+            pflag[t] = any_exc;
+            if (any_exc) {
+                const WorkList& pl = ((tz + ty + tx) & 1) ? pl1 : pl0;
+                pl.items[atomicAdd(pl.count, 1)] = t;
+            }
+        }
+    }
+}
+
+template <typename E>
+constexpr size_t build_smem_bytes()
+{
+    return (size_t)((BUILD_HZ * BUILD_HY * BUILD_BX * sizeof(E) + 127) / 128 * 128) + (2 * 9 * 32 + 2 * 8 * 33) * sizeof(double) + 8 + 8 * sizeof(int) +
+           8 * sizeof(double) + 64;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// marker volumes -> bit planes (device side; the host binding packs on the CPU for the end-to-end path so that the
+// markers cross PCIe as 0.25 B/voxel instead of 2): bit (v & 31) of word (v >> 5) = marker[v] != 0
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack_bits(const uint8_t* __restrict__ src, unsigned n, unsigned* __restrict__ dst)
+{
+    const unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = v < n && src[v] != 0;
+    const unsigned w = __ballot_sync(0xffffffffu, on);
+    if ((threadIdx.x & 31) == 0 && v < n) dst[v >> 5] = w;
+}

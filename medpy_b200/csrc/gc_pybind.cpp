@@ -148,6 +148,32 @@ public:
         { py::gil_scoped_release rel; rc = mgc_add_boundary(g_, kind, &r.a, sigma, sp.empty() ? nullptr : sp.data(), norm); }
         check(rc, g_);
     }
+    // everything graph_from_voxels adds, in one native call (mgc_build_voxel_graph); None = term absent, kind -1 = no boundary
+    void build_voxel_graph(const py::object& prob, double alpha, bool compute_f32, int kind, const py::object& image, double sigma,
+                           const py::object& spacing, double norm, const py::object& fg, const py::object& bg)
+    {
+        ArrayRef rp, ri, rf, rb;
+        mgc_voxel_terms t{};
+        t.alpha = alpha;
+        t.compute_dtype = compute_f32 ? MGC_F32 : MGC_F64;
+        t.boundary_kind = kind;
+        t.sigma = sigma;
+        t.norm = norm;
+        if (!prob.is_none()) { rp = make_ref(prob, -1, "probability_map"); check_shape(rp, "probability_map"); t.prob = &rp.a; }
+        if (!image.is_none()) { ri = make_ref(image, -1, "image"); check_shape(ri, "image"); t.image = &ri.a; }
+        if (!fg.is_none()) { rf = make_ref(fg, MGC_U8, "fg_markers"); check_shape(rf, "fg_markers"); t.fg = &rf.a; }
+        if (!bg.is_none()) { rb = make_ref(bg, MGC_U8, "bg_markers"); check_shape(rb, "bg_markers"); t.bg = &rb.a; }
+        std::vector<double> sp;
+        if (!spacing.is_none()) {
+            sp = spacing.cast<std::vector<double>>();
+            if (sp.size() < shape_.size()) throw py::value_error("spacing has fewer entries than the image has dimensions");
+            t.spacing = sp.data();
+        }
+        int rc;
+        { py::gil_scoped_release rel; rc = mgc_build_voxel_graph(g_, &t); }
+        check(rc, g_);
+    }
+    bool can_fuse() const { return mgc_can_fuse(g_) != 0; }
     void add_nweights_dense(int axis, const py::object& fwd, const py::object& bwd)
     {
         ArrayRef a = make_ref(fwd, MGC_F64, "fwd"), b = make_ref(bwd, MGC_F64, "bwd");
@@ -490,6 +516,8 @@ PYBIND11_MODULE(_mgc, m)
         .def("add_markers", &PyGraph::add_markers)
         .def("add_boundary", &PyGraph::add_boundary)
         .def("add_nweights_dense", &PyGraph::add_nweights_dense)
+        .def("build_voxel_graph", &PyGraph::build_voxel_graph)
+        .def("can_fuse", &PyGraph::can_fuse)
         .def("maxflow", &PyGraph::maxflow)
         .def("get_mask", &PyGraph::get_mask)
         .def("get_mask_into", &PyGraph::get_mask_into)

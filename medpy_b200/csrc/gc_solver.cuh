@@ -155,7 +155,9 @@ __global__ void __launch_bounds__(256) k_count_active(Lattice L, State<T> S, uns
 // ---------------------------------------------------------------------------------------------------
 // mask[v] = 1 unless v can reach the sink (bin/medpy_graphcut_voxel.py:177-181 with graph.h:560-571), fused with the
 // energy reduction: flow absorbed by the sink links of the owned voxels (fixed-order fp64 sums, deterministic)
-template <typename T>
+// LAZY: sink[v] holds a value only where rmask bit 7 (RM_SINKV, gc_tiles.cuh) is set -- the 3-D tile solver never
+// zero-fills the array, and only the voxels that absorbed flow are read here (4 + 1 B/voxel instead of 4 + 8).
+template <typename T, bool LAZY>
 __global__ void __launch_bounds__(256) k_readout(Lattice L, State<T> S, uint8_t* __restrict__ mask, double* __restrict__ partials)
 {
     __shared__ double sh[8];
@@ -170,7 +172,14 @@ __global__ void __launch_bounds__(256) k_readout(Lattice L, State<T> S, uint8_t*
         m.z = h.z >= MGC_HINF ? 1 : 0; m.w = h.w >= MGC_HINF ? 1 : 0;
         reinterpret_cast<uchar4*>(mask)[q] = m;
         const unsigned v = q << 2;
-        if (sizeof(T) == 8) {
+        if (LAZY) {
+            const unsigned r4 = reinterpret_cast<const unsigned*>(S.rmask)[q] & 0x80808080u;
+            if (r4) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if ((r4 >> (8 * i + 7)) & 1u) { if (owned(L, v + i)) a = __dadd_rn(a, (double)S.sink[v + i]); }
+            }
+        } else if (sizeof(T) == 8) {
             const double2 s0 = reinterpret_cast<const double2*>(S.sink)[2 * q];
             const double2 s1 = reinterpret_cast<const double2*>(S.sink)[2 * q + 1];
             if (owned(L, v)) a = __dadd_rn(a, s0.x);
@@ -185,7 +194,7 @@ __global__ void __launch_bounds__(256) k_readout(Lattice L, State<T> S, uint8_t*
     if (blockIdx.x == 0 && threadIdx.x < (L.n & 3u)) {
         const unsigned v = (n4 << 2) + threadIdx.x;
         mask[v] = S.height[v] >= MGC_HINF ? 1 : 0;
-        if (owned(L, v)) a = __dadd_rn(a, (double)S.sink[v]);
+        if (owned(L, v) && (!LAZY || (S.rmask[v] & 0x80u))) a = __dadd_rn(a, (double)S.sink[v]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a = __dadd_rn(a, __shfl_down_sync(0xffffffffu, a, o));

@@ -30,6 +30,7 @@
 #define HALO_DIM 10
 #define HALO_VOX 1000
 #define RM_SINK 0x40u   // bit 6 of rmask: residual capacity towards the sink
+#define RM_SINKV 0x80u  // bit 7 of rmask: sink[v] (flow absorbed so far) has been written; unset = 0, the array is never zero-filled
 
 struct Tiles {
     int nt[3];      // tiles along z, y, x
@@ -134,7 +135,8 @@ __device__ __forceinline__ int fetch_tile(const WorkList& cur, int* __restrict__
 // ---------------------------------------------------------------------------------------------------
 // init: one pass over every tile after the terms are in
 //   excess = min(max(tr,0), roundup(sum of out-capacities))   (source-link clamp)
-//   sink[] = 0 (flow absorbed so far), rmask, first labels (1 where a sink link exists, else HINF)
+//   sink[] (flow absorbed so far) is NOT written: rmask bit RM_SINKV marks entries that hold a value
+//   rmask, first labels (1 where a sink link exists, else HINF)
 //   relabel worklist <- tiles holding an unlabelled voxel with residual out-arcs
 //   push worklists   <- tiles holding a voxel with excess
 // ---------------------------------------------------------------------------------------------------
@@ -159,8 +161,7 @@ __global__ void __launch_bounds__(TILE_VOX) k_init_tile(Lattice L, Tiles TL, Sta
         if (tr < 0) m |= RM_SINK;
         if (!c.own) e = 0.0;
         S.excess[c.v] = (T)e;
-        S.sink[c.v] = (T)0;
-        S.rmask[c.v] = (uint8_t)m;
+        S.rmask[c.v] = (uint8_t)m;          // RM_SINKV clear: sink[v] counts as 0 without being written
         const int h = (c.own && tr < 0) ? 1 : MGC_HINF;
         S.height[c.v] = h;
         needs = (c.own && (m & 0x3fu) != 0 && h == MGC_HINF) ? 1 : 0;
@@ -351,6 +352,7 @@ __device__ __forceinline__ void push_visit_staged(const Lattice& L, const Tiles&
     if (tid == 0) pflag[t] = 0;
     const int h0 = load_heights(L, c, S.height, s_h);
     T e = 0, scap = 0, sf = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
+    unsigned sinkv = 0;                     // RM_SINKV of this voxel (sink[v] holds a value)
     if (c.inb) {
         if (stg) {
             c0 = (T)stg[0 * TILE_VOX + tid]; c1 = (T)stg[1 * TILE_VOX + tid]; c2 = (T)stg[2 * TILE_VOX + tid];
@@ -362,7 +364,11 @@ __device__ __forceinline__ void push_visit_staged(const Lattice& L, const Tiles&
             c3 = S.cap[3][c.v]; c4 = S.cap[4][c.v]; c5 = S.cap[5][c.v];
         }
         const T tr = S.tr[c.v];
-        if (tr < 0) { scap = -tr; sf = S.sink[c.v]; }
+        if (tr < 0) {
+            scap = -tr;
+            sinkv = S.rmask[c.v] & RM_SINKV;
+            if (sinkv) sf = S.sink[c.v];
+        }
     }
     int h = h0;
     unsigned nbr_listed = 0, dirty = 0;     // dirty: bit k = cap k changed, 64 = excess, 128 = sink flow
@@ -411,9 +417,9 @@ __device__ __forceinline__ void push_visit_staged(const Lattice& L, const Tiles&
         if (dirty & 16u) S.cap[4][c.v] = c4;
         if (dirty & 32u) S.cap[5][c.v] = c5;
         if (h != h0) S.height[c.v] = h;
-        if (dirty & 128u) S.sink[c.v] = sf;
+        if (dirty & 128u) { S.sink[c.v] = sf; sinkv = RM_SINKV; }
         unsigned m = (c0 > 0 ? 1u : 0u) | (c1 > 0 ? 2u : 0u) | (c2 > 0 ? 4u : 0u) | (c3 > 0 ? 8u : 0u) |
-                     (c4 > 0 ? 16u : 0u) | (c5 > 0 ? 32u : 0u) | ((scap - sf > 0) ? RM_SINK : 0u);
+                     (c4 > 0 ? 16u : 0u) | (c5 > 0 ? 32u : 0u) | ((scap - sf > 0) ? RM_SINK : 0u) | sinkv;
         S.rmask[c.v] = (uint8_t)m;
     }
     const int still = (c.own && e > 0 && h < MGC_HINF) ? 1 : 0;

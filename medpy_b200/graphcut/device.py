@@ -44,12 +44,13 @@ def graph_from_device_arrays(fg_markers, bg_markers, image=None, boundary=None, 
     nat = graph._nat()
     if stream is not None:
         nat.set_stream(int(stream))
-    if prob is not None:
-        compute_f32 = "float32" in str(prob.dtype)
-        nat.add_regional_probability(prob, float(alpha), compute_f32)
-    if boundary is not None:
-        kind = _KINDS[boundary]
-        sp = [float(s) for s in spacing] if spacing else None
-        nat.add_boundary(kind, image, 0.0 if sigma is None else float(sigma), sp, math.nan)
-    nat.add_markers(_as_u8(fg_markers), _as_u8(bg_markers))
+    graph._fresh = False
+    # one native call: single-pass fused build on 1-D..3-D lattices (mgc_build_voxel_graph), the per-term kernels in
+    # the reference's order otherwise.  A non-positive n-link weight is reported by maxflow() (ValueError).
+    graph.defer_weight_check(True)
+    compute_f32 = prob is not None and "float32" in str(prob.dtype)
+    kind = _KINDS[boundary] if boundary is not None else -1
+    sp = [float(s) for s in spacing] if spacing else None
+    nat.build_voxel_graph(prob, 0.0 if alpha is None else float(alpha), compute_f32, kind, image,
+                          0.0 if sigma is None else float(sigma), sp, math.nan, _as_u8(fg_markers), _as_u8(bg_markers))
     return graph

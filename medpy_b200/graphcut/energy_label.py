@@ -65,6 +65,8 @@ class LabelContext:
         a = numpy.asarray(array)
         if a.shape != self.shape:
             raise ValueError("{} of shape {} does not match the label image of shape {}".format(what, a.shape, self.shape))
+        if not a.dtype.isnative:                       # '>f4', '>i2' (FITS / NIfTI readers): the kernels read native values
+            a = a.astype(a.dtype.newbyteorder("="))
         if a.dtype == numpy.bool_:
             a = a.view(numpy.uint8)
         if a.dtype.type not in _DEVICE_DTYPES:

@@ -34,10 +34,18 @@ _DIFF_LINEAR, _DIFF_EXP, _DIFF_DIV, _DIFF_POW, _MAX_LINEAR, _MAX_EXP, _MAX_DIV, 
 _DEVICE_DTYPES = (numpy.float32, numpy.float64, numpy.uint8, numpy.int16, numpy.int32)
 
 
+def _native_order(a):
+    """Arrays in non-native byte order ('>f4', '>i2': FITS / NIfTI readers) are converted once; the kernels read native
+    values only (the reference goes through numpy, which handles the byte order)."""
+    if not a.dtype.isnative:
+        return a.astype(a.dtype.newbyteorder("="))
+    return a
+
+
 def _device_image(image):
     """Images whose dtype the kernels read natively pass through untouched (any strides); the rest are widened
     to float64 on the host, which is what the reference does to every image anyway (energy_voxel.py:634)."""
-    image = numpy.asarray(image)
+    image = _native_order(numpy.asarray(image))
     if image.dtype == numpy.bool_:
         return image.view(numpy.uint8)
     if image.dtype.type in _DEVICE_DTYPES and all(s > 0 for s in image.strides):
@@ -57,7 +65,7 @@ def _spacing_arg(spacing, ndim):
 
 
 def _boundary(graph, kind, image, sigma, spacing):
-    image = numpy.asarray(image)
+    image = _native_order(numpy.asarray(image))
     # linear normaliser M, formed in the image's own dtype (energy_voxel.py:99, :174).  float32/float64 images:
     # NaN asks the device to do the min/max reduction (kernel K0, same dtype arithmetic); integer images:
     # numpy on the host so narrow-integer wrap-around matches the reference exactly.
@@ -73,14 +81,14 @@ def _boundary(graph, kind, image, sigma, spacing):
     graph._add_boundary(kind, dev, 0.0 if sigma is None else float(sigma), _spacing_arg(spacing, image.ndim), norm)
 
 
-def regional_probability_map(graph, xxx_todo_changeme):
+def regional_probability_map(graph, term_args):
     """Regional term based on a probability atlas (reference: energy_voxel.py:33-65).
 
     ``term_args = (probability_map, alpha)``; every voxel gets the t-weights
     ``(p * alpha, (1 - p) * alpha)`` (source = foreground, sink = background) through
     ``graph.set_tweights_all`` semantics, i.e. ``add_tweights`` per voxel in node order."""
-    (probability_map, alpha) = xxx_todo_changeme
-    probability_map = numpy.asarray(probability_map)
+    (probability_map, alpha) = term_args
+    probability_map = _native_order(numpy.asarray(probability_map))
     # dtype numpy gives the two products (numpy-2 weak scalars: float32 map * Python float stays float32)
     src_dtype = (probability_map[:0] * alpha).dtype
     snk_dtype = ((1 - probability_map[:0]) * alpha).dtype
@@ -94,57 +102,57 @@ def regional_probability_map(graph, xxx_todo_changeme):
                                  ((1 - probability_map) * alpha).astype(numpy.float64).ravel())
 
 
-def boundary_maximum_linear(graph, xxx_todo_changeme1):
+def boundary_maximum_linear(graph, term_args):
     """Boundary term on the gradient image, linear (reference: energy_voxel.py:68-116).
     ``term_args = (gradient_image, spacing)``."""
-    (gradient_image, spacing) = xxx_todo_changeme1
+    (gradient_image, spacing) = term_args
     _boundary(graph, _MAX_LINEAR, gradient_image, None, spacing)
 
 
-def boundary_difference_linear(graph, xxx_todo_changeme2):
+def boundary_difference_linear(graph, term_args):
     """Boundary term on intensity differences, linear (reference: energy_voxel.py:119-191).
     ``term_args = (original_image, spacing)``."""
-    (original_image, spacing) = xxx_todo_changeme2
+    (original_image, spacing) = term_args
     _boundary(graph, _DIFF_LINEAR, original_image, None, spacing)
 
 
-def boundary_maximum_exponential(graph, xxx_todo_changeme3):
+def boundary_maximum_exponential(graph, term_args):
     """Boundary term on the gradient image, exponential (reference: energy_voxel.py:194-238).
     ``term_args = (gradient_image, sigma, spacing)``."""
-    (gradient_image, sigma, spacing) = xxx_todo_changeme3
+    (gradient_image, sigma, spacing) = term_args
     _boundary(graph, _MAX_EXP, gradient_image, sigma, spacing)
 
 
-def boundary_difference_exponential(graph, xxx_todo_changeme4):
+def boundary_difference_exponential(graph, term_args):
     """Boundary term on intensity differences, exponential (reference: energy_voxel.py:241-302).
     ``term_args = (original_image, sigma, spacing)``."""
-    (original_image, sigma, spacing) = xxx_todo_changeme4
+    (original_image, sigma, spacing) = term_args
     _boundary(graph, _DIFF_EXP, original_image, sigma, spacing)
 
 
-def boundary_maximum_division(graph, xxx_todo_changeme5):
+def boundary_maximum_division(graph, term_args):
     """Boundary term on the gradient image, division (reference: energy_voxel.py:305-349; the reference
     evaluates the *difference* skeleton here, :347, and so do we).  ``term_args = (gradient_image, sigma, spacing)``."""
-    (gradient_image, sigma, spacing) = xxx_todo_changeme5
+    (gradient_image, sigma, spacing) = term_args
     _boundary(graph, _MAX_DIV, gradient_image, sigma, spacing)
 
 
-def boundary_difference_division(graph, xxx_todo_changeme6):
+def boundary_difference_division(graph, term_args):
     """Boundary term on intensity differences, division (reference: energy_voxel.py:352-409).
     ``term_args = (original_image, sigma, spacing)``."""
-    (original_image, sigma, spacing) = xxx_todo_changeme6
+    (original_image, sigma, spacing) = term_args
     _boundary(graph, _DIFF_DIV, original_image, sigma, spacing)
 
 
-def boundary_maximum_power(graph, xxx_todo_changeme7):
+def boundary_maximum_power(graph, term_args):
     """Boundary term on the gradient image, power (reference: energy_voxel.py:412-454).
     ``term_args = (gradient_image, sigma, spacing)``."""
-    (gradient_image, sigma, spacing) = xxx_todo_changeme7
+    (gradient_image, sigma, spacing) = term_args
     _boundary(graph, _MAX_POW, gradient_image, sigma, spacing)
 
 
-def boundary_difference_power(graph, xxx_todo_changeme8):
+def boundary_difference_power(graph, term_args):
     """Boundary term on intensity differences, power (reference: energy_voxel.py:457-516).
     ``term_args = (original_image, sigma, spacing)``."""
-    (original_image, sigma, spacing) = xxx_todo_changeme8
+    (original_image, sigma, spacing) = term_args
     _boundary(graph, _DIFF_POW, original_image, sigma, spacing)

@@ -72,6 +72,11 @@ class GraphDouble:
         self._offlattice = None
         self._pending = []
         self._defer_weight_check = False
+        # whole-lattice terms collected while graph_from_voxels runs (regional, boundary, markers): handed to the device
+        # in ONE native call (mgc_build_voxel_graph: single-pass fused build) when the markers arrive or anything else
+        # needs the graph.  Only while nothing has reached the device yet (_fresh).
+        self._lazy = None
+        self._fresh = True
         if sparse:
             if self._journal is None:
                 raise ValueError("a lattice shape and sparse=True exclude each other")
@@ -120,14 +125,44 @@ class GraphDouble:
         """Let a boundary term return before its kernel has reported non-positive weights; the ValueError is then
         raised by the next call on the graph (graph_from_voxels adds the markers right after the boundary term, so the
         marker upload overlaps the stencil kernel).  ``check_deferred()`` forces the verdict."""
+        if not on:
+            self._commit()
         self._defer_weight_check = bool(on)
         if self._native is not None:
             from .. import _lib
             self._native.set_option(_lib._mgc.OPT_DEFER_WEIGHT_CHECK, 1 if on else 0)
 
     def check_deferred(self):
+        self._commit()
         if self._native is not None:
             self._native.check_deferred()
+
+    # ------------------------------------------------------------------ collected whole-lattice terms
+    def _collect(self, key, value):
+        """Record a whole-lattice term instead of launching it; False if it has to run right away (the graph already
+        holds terms, element-wise calls are staged, the same kind of term was collected before, or collection is off)."""
+        if not self._defer_weight_check or not self._fresh or self._sp is not None:
+            return False
+        if self._st_src is not None or self._st_nw or self._pending:
+            return False
+        if self._lazy is not None and key in self._lazy:
+            return False
+        if self._lazy is None:
+            self._lazy = {}
+        self._lazy[key] = value
+        return True
+
+    def _commit(self):
+        """Hand the collected terms to the device: regional term, boundary term, fg / bg markers in the reference's
+        order (generate.py:159-172), as one fused pass where the native side can (mgc_build_voxel_graph)."""
+        lazy, self._lazy = self._lazy, None
+        if not lazy:
+            return
+        self._fresh = False
+        prob, alpha, f32 = lazy.get("reg", (None, 0.0, False))
+        kind, image, sigma, spacing, norm = lazy.get("bnd", (-1, None, 0.0, None, float("nan")))
+        fg, bg = lazy.get("mark", (None, None))
+        self._nat().build_voxel_graph(prob, float(alpha), bool(f32), int(kind), image, float(sigma), spacing, float(norm), fg, bg)
 
     def _dirty(self):
         self._mask = None
@@ -167,6 +202,7 @@ class GraphDouble:
                 self._add_tweights_staged(int(v), cap_source, cap_sink)
 
     def _flush(self):
+        self._commit()
         self._close_tweight_batch()
         if self._st_nw:
             for axis in sorted(self._st_nw):
@@ -174,6 +210,8 @@ class GraphDouble:
                 self._pending.append(("nw", axis, fwd, bwd))
             self._st_nw = {}
         pending, self._pending = self._pending, []
+        if pending:
+            self._fresh = False
         for op in pending:
             if op[0] == "tw":
                 self._nat().add_tweights_dense(op[1].reshape(self._shape), op[2].reshape(self._shape))
@@ -190,8 +228,11 @@ class GraphDouble:
 
     def add_regional_probability(self, prob, alpha, compute_f32):
         self._lattice_term()
-        self._flush()
         self._dirty()
+        if self._collect("reg", (self._positive_strides(prob), float(alpha), bool(compute_f32))):
+            return
+        self._flush()
+        self._fresh = False
         self._nat().add_regional_probability(self._positive_strides(prob), float(alpha), bool(compute_f32))
 
     def add_tweights_dense(self, src, snk):
@@ -210,6 +251,7 @@ class GraphDouble:
             return
         self._flush()
         self._dirty()
+        self._fresh = False
         self._nat().add_tweights_dense(src, snk)
 
     @staticmethod
@@ -224,20 +266,27 @@ class GraphDouble:
 
     def add_markers(self, fg, bg):
         self._lattice_term()
-        self._flush()
         self._dirty()
+        if self._lazy and "mark" not in self._lazy and self._collect("mark", (self._positive_strides(fg), self._positive_strides(bg))):
+            return self._commit()        # the markers are graph_from_voxels' last step: build now
+        self._flush()
+        self._fresh = False
         self._nat().add_markers(self._positive_strides(fg), self._positive_strides(bg))
 
     def add_boundary(self, kind, image, sigma, spacing, norm):
         self._lattice_term()
-        self._flush()
         self._dirty()
+        if self._collect("bnd", (int(kind), self._positive_strides(image), float(sigma), spacing, float(norm))):
+            return
+        self._flush()
+        self._fresh = False
         self._nat().add_boundary(int(kind), self._positive_strides(image), float(sigma), spacing, float(norm))
 
     def add_nweights_dense(self, axis, fwd, bwd):
         self._lattice_term()
         self._flush()
         self._dirty()
+        self._fresh = False
         self._nat().add_nweights_dense(int(axis), fwd, bwd)
 
     # ------------------------------------------------------------------ reference GraphDouble API
@@ -364,6 +413,8 @@ class GraphDouble:
         self._mask = None
         self._offlattice = None
         self._pending = []
+        self._lazy = None
+        self._fresh = True
         if self._native is not None:
             self._native.reset()
 

@@ -51,7 +51,8 @@ def graphcut_stawiaski(regions, gradient=False, foreground=False, background=Fal
 
 def graphcut_subprocesses(graphcut_function, graphcut_arguments, processes=None):
     """``[graphcut_function(a) for a in graphcut_arguments]`` (wrapper.py:228-268), one after the other on the GPU."""
-    if processes is not None and processes is not False and (type(processes) is not int or processes <= 0):
+    # the reference treats every falsy value as "use cpu_count" (`if not processes`, wrapper.py:252) and validates the rest
+    if processes and (type(processes) is not int or processes < 0):
         raise ArgumentError("The number processes can not be zero or negative.")
     return [graphcut_function(a) for a in graphcut_arguments]
 

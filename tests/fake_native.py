@@ -193,6 +193,17 @@ class FakeGraph:
             self.wb[d] += full
         self.result = None
 
+    def build_voxel_graph(self, prob, alpha, compute_f32, kind, image, sigma, spacing, norm, fg, bg):
+        """mgc_build_voxel_graph: the three terms in the reference's order."""
+        if prob is not None:
+            self.add_regional_probability(prob, alpha, compute_f32)
+        if kind >= 0:
+            self.add_boundary(kind, image, sigma, spacing, norm)
+        self.add_markers(fg, bg)
+
+    def can_fuse(self):
+        return False
+
     def add_nweights_dense(self, axis, fwd, bwd):
         fwd, bwd = numpy.asarray(fwd, dtype=float).ravel(), numpy.asarray(bwd, dtype=float).ravel()
         if (fwd < 0).any() or (bwd < 0).any():

@@ -25,13 +25,13 @@ def test_cabi_exports_every_declared_symbol():
     missing = [name for name in declared if not hasattr(lib, name)]
     assert not missing, missing
     lib.mgc_abi_version.restype = ctypes.c_int
-    assert lib.mgc_abi_version() == 2
+    assert lib.mgc_abi_version() == 3
 
 
 def test_pybind_module_imports_and_matches_abi():
     _ensure_built()
     from medpy_b200 import _lib
-    assert _lib.ABI_VERSION == 2 and _lib.SOURCE == 0 and _lib.SINK == 1
+    assert _lib.ABI_VERSION == 3 and _lib.SOURCE == 0 and _lib.SINK == 1
 
 
 def test_no_cpu_fallback_without_device():
