@@ -1,21 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- Mvoxels/s to converged min-cut (BASELINE.json metric) on the headline workload.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size S] [--no-extras]
 
-A "step" is one complete pass of the hot path over one synthetic volume: energy terms (n-link stencil,
-regional t-links, markers) -> max-flow to convergence -> mask + energy.  Workload (config.workload): BASELINE
-config 3, a 512^3 fp32 two-blob volume with regional_probability_map t-links + boundary_difference_exponential
-(sigma = RMS neighbour difference), fg ball / bg shell markers.
+A "step" is one complete pass of the hot path over one synthetic volume: graph build (n-link stencil, regional
+t-links, markers, solver state -- one fused kernel) -> max-flow to convergence -> mask + energy.  Workload
+(config.workload): BASELINE config 3, a 512^3 fp32 two-blob volume with regional_probability_map t-links +
+boundary_difference_exponential (sigma = RMS neighbour difference), fg ball / bg shell markers.
 
-  value   : N_voxels * K / t, inputs resident in HBM, t = CUDA events around the K timed steps (max over ranks)
-  e2e     : same metric through the public API (medpy_b200.graphcut.graph_from_voxels -> maxflow -> get_mask)
-            from pinned HOST buffers, H2D and D2H inside the timed region
-  roofline: dominant kernel class (push sweep or relabel sweep), algorithmic bytes / measured launch time
-  cpu_baseline: the reference's BK solver (oracle/_ref, real reference sources) or the oracle port, timed on a
-            bounded sample (a 256^3 volume of the same generator) on the host, 1 thread (BK is serial)
+  value    : N_voxels * K / t, inputs resident in HBM, t = CUDA events around the K timed steps (max over ranks)
+  e2e      : same metric through the public API (medpy_b200.graphcut.graph_from_voxels -> maxflow -> get_mask)
+             from pinned HOST buffers, H2D and D2H inside the timed region
+  roofline : the dominant kernel by device time (k_build_tile, the fused graph build): algorithmic bytes per launch /
+             its CUDA-event time, measured live; `traffic` = its DRAM bytes per launch from the committed ncu capture.
+             `roofline_maxflow` = the max-flow phase (global relabels + push passes + stop tests): measured DRAM bytes
+             of those kernels (same capture) / their live device time.  Same choice at every N (rank 0's slab).
+  mask_sha256 : sha256 of the full uint8 mask of the last timed step, at every N, next to the committed hash of the
+             REFERENCE solver's mask on this workload (tests/golden/bench_mask_sha256.json; pinned by
+             tests/test_gpu_fullsize.py) -- `mask_matches_reference`
+  config.extra : the other BASELINE configs, measured once each outside the timed region of the headline:
+             N = 1: config 2 (256^3 boundary only), config 4 (256x256x128x4, 4-D), config 5 on ONE GPU (its oracle);
+             N > 1: config 5 (1024^3) z-slab partitioned over the N GPUs
+  cpu_baseline: the reference's BK solver (oracle/_ref, real reference sources) timed on a bounded 256^3 sample of the
+             same generator on the host, 1 thread (BK is serial)
 
-`--impl reference` times only that CPU arm (rank 0; other ranks exit 0).
+`--impl reference` times the reference's CPU path on the SAME 512^3 instance (numpy terms + C++ graph fill + BK maxflow +
+read-out; ~40 s and ~40 GB of host memory per step, so at most 2 steps are measured whatever K says -- stated in the line).
 N > 1: the volume is z-slab partitioned over the ranks (one process per GPU, NCCL halo exchange of border
 heights / pushed flow); same total work => "scaling": "strong".
 """
@@ -143,47 +153,75 @@ def cpu_reference_run(size, repeats=1):
             fill, mf, ro = tm["setup_s"], tm["maxflow_s"], 0.0
         total = (t1 - t0) + fill + mf + ro
         r = dict(kind=kind, n=n, terms_s=t1 - t0, fill_s=fill, maxflow_s=mf, readout_s=ro, total_s=total,
-                 energy=flow, fg_voxels=int(mask.sum()))
+                 energy=flow, fg_voxels=int(mask.sum(dtype=numpy.int64)), mask_sha256=sha256_of(mask))
         if best is None or r["total_s"] < best["total_s"]:
             best = r
     return best
 
 
-def cpu_baseline_obj(r, size):
+def workload_text(size, sigma=None):
+    t = ("BASELINE config 3: %d^3 fp32 two-blob volume, regional_probability_map (alpha 0.1) + boundary_difference_exponential "
+         "(sigma = RMS neighbour difference), fg balls / bg shell" % size)
+    return t
+
+
+def cpu_baseline_obj(r, size, workload_size):
+    frac = (float(size) / workload_size) ** 3
     return {
         "value": r["n"] / r["total_s"] / 1e6, "unit": UNIT, "cores": 1, "kind": r["kind"],
-        "sample": "%d^3 two-blob volume, same generator and terms as the workload (1/%d of its voxels); "
+        "sample": "%d^3 two-blob volume, same generator and terms as the workload (%s of its voxels); "
                   "numpy terms %.2fs + C++ graph fill %.2fs + BK maxflow() %.2fs + read-out %.2fs"
-                  % (size, max(1, (512 // size) ** 3), r["terms_s"], r["fill_s"], r["maxflow_s"], r["readout_s"]),
+                  % (size, "all" if frac >= 1.0 else "1/%d" % round(1.0 / frac), r["terms_s"], r["fill_s"], r["maxflow_s"], r["readout_s"]),
         "maxflow_only_value": r["n"] / max(r["maxflow_s"], 1e-9) / 1e6,
         "host_cores_available": os.cpu_count(),
     }
 
 
+def committed_mask_hash(key="config3_512"):
+    try:
+        return json.load(open(os.path.join(ROOT, "tests", "golden", "bench_mask_sha256.json")))[key]["sha256"]
+    except Exception:
+        return None
+
+
+def sha256_of(arr):
+    import hashlib
+    return hashlib.sha256(numpy.ascontiguousarray(arr, dtype=numpy.uint8).tobytes()).hexdigest()
+
+
 def run_reference_arm(args):
+    """The reference's own CPU implementation of the path on the SAME instance as the GPU arm (same_config): numpy terms,
+    C++ graph fill, BK maxflow(), what_segment read-out -- oracle/_ref = lib/maxflow/src compiled in place.  One step at
+    512^3 is ~40 s and ~40 GB of host memory, so the number of measured steps is capped (config.steps_measured)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    size = args.cpu_size
-    # warm-up + timed steps, each step one bounded sample
-    for _ in range(max(0, min(args.warmup, 1))):
+    size = args.cpu_size if args.cpu_size else args.size
+    cap = 2 if size >= 384 else (5 if size >= 200 else args.steps)
+    steps = max(1, min(args.steps, cap))
+    warm = 0 if size >= 384 else max(0, min(args.warmup, 1))
+    for _ in range(warm):
         cpu_reference_run(size)
     t0 = time.time()
-    rs = [cpu_reference_run(size) for _ in range(args.steps)]
+    rs = [cpu_reference_run(size) for _ in range(steps)]
     dt = time.time() - t0
     n = rs[0]["n"]
     total = sum(r["total_s"] for r in rs)
     value = n * len(rs) / total / 1e6
     best = min(rs, key=lambda r: r["total_s"])
-    cb = cpu_baseline_obj(best, size)
+    cb = cpu_baseline_obj(best, size, args.size)
     cb["value"] = value
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(rs), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "BASELINE config 3 terms (regional_probability_map + boundary_difference_exponential, "
-                               "sigma=RMS) on a bounded %d^3 sample of the 512^3 two-blob fp32 volume" % size,
-                   "solver": "reference BK (lib/maxflow/src, -O2 -DNDEBUG)" if best["kind"] == "reference" else "oracle BK port",
+        "config": {"workload": workload_text(size), "shape": [size] * 3, "state_dtype": "float64", "parallelism": "single",
+                   "solver": "reference BK (lib/maxflow/src, -O2 -DNDEBUG), 1 host thread (BK is serial)"
+                             if best["kind"] == "reference" else "oracle BK port",
+                   "steps_measured": len(rs), "warmup_measured": warm,
+                   "steps_note": "one step = the whole %d^3 instance on one host core; capped at %d measured steps so the arm "
+                                 "finishes within minutes" % (size, cap),
+                   "energy": best["energy"], "fg_voxels": best["fg_voxels"], "mask_sha256": best.get("mask_sha256"),
                    "wall_s": dt},
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -196,6 +234,52 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
+def traffic_table():
+    """DRAM bytes per launch / per step from the committed `ncu --set full` capture of this workload (profiles/)."""
+    for name in ("r02_traffic_512cubed.json", "r01_traffic_512cubed.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))
+            t["_file"] = "profiles/" + name
+            return t
+        except Exception:
+            continue
+    return {}
+
+
+BUILD_BYTES_PER_VOXEL = 79    # k_build_tile: image 4 + prob 4 + fg 1 + bg 1 read; 6 caps 48 + tr 8 + excess 8 + label 4 + rmask 1 written
+BUILD_BYTES_NOREG = 75        # ... without the regional term (no probability map)
+
+
+def rooflines(stats_list, n_local, n_global, peak, peak_kind, regional=True):
+    """`roofline`: k_build_tile (dominant kernel by device time).  `roofline_maxflow`: the max-flow phase."""
+    k = max(len(stats_list), 1)
+    tt = traffic_table()
+    ms_build = sum(s["ms_boundary"] for s in stats_list) / k
+    bpv = BUILD_BYTES_PER_VOXEL if regional else BUILD_BYTES_NOREG
+    alg = n_local * bpv
+    ach = alg / (ms_build * 1e-3) / 1e9 if ms_build > 0 else 0.0
+    per_launch = tt.get("bytes_per_launch", {})
+    traffic = per_launch.get("k_build_tile") if n_local == 512 ** 3 else None
+    ms_rel = sum(s["ms_relabel"] for s in stats_list) / k
+    ms_push = sum(s["ms_push"] for s in stats_list) / k
+    ms_solve = sum(s["ms_solve"] for s in stats_list) / k
+    ms_read = sum(s["ms_readout"] for s in stats_list) / k
+    share = {"k_build_tile_ms": ms_build, "relabel_ms": ms_rel, "push_ms": ms_push, "solve_ms": ms_solve, "readout_ms": ms_read,
+             "note": "device ms per step from the library's CUDA events (mgc_stats); solve = relabels + pushes + stop tests"}
+    roof = {"bound": "hbm", "kernel": "k_build_tile (fused graph build: n-link stencil + t-links + markers + solver state)",
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_kind": peak_kind,
+            "launches": k, "avg_launch_ms": ms_build, "algorithmic_bytes_per_launch": alg,
+            "algorithmic_bytes_per_voxel": bpv, "traffic_source": tt.get("_file"), "share_of_step": share}
+    mf_bytes = tt.get("maxflow_phase_bytes_per_step") if n_global == 512 ** 3 and n_local == n_global else None
+    mf = {"bound": "hbm", "kernel": "max-flow phase: k_bfs_coop / k_relabel_reset / k_sweep_* (global relabel) + k_push_tile_tma + k_count_active_tiles",
+          "measured_dram_bytes_per_step": mf_bytes, "ms_per_step": ms_solve,
+          "achieved": (mf_bytes / (ms_solve * 1e-3) / 1e9) if (mf_bytes and ms_solve > 0) else None, "peak": peak, "unit": "GB/s",
+          "frac": (mf_bytes / (ms_solve * 1e-3) / 1e9 / peak) if (mf_bytes and ms_solve > 0) else None,
+          "note": "worklist kernels touch only active tiles: the phase is latency-bound (grid barriers, tile visits), not bandwidth-bound; "
+                  "bytes are MEASURED dram__bytes of those launches (ncu), time is live"}
+    return roof, mf
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -213,130 +297,146 @@ def run_gpu_arm(args):
     n = int(numpy.prod(shape))
     peak, peak_kind = measured_peak()
 
+    extras = {}
     if world > 1:
         from medpy_b200 import distributed as mdist
         result = mdist.bench_slab(shape, args, rank, world, local_rank)   # each rank builds only its own planes
         vol = {"sigma": result["sigma"]}
+        if not args.no_extras:
+            extras["config5_1024cubed_zslab%d" % world] = mdist.bench_config5(args, rank, world, local_rank)
     else:
         vol = make_volume(size)
         result = bench_single(vol, args, torch)
+        del vol["image"], vol["prob"], vol["fg"], vol["bg"]
+        if not args.no_extras:
+            extras = run_extras_single(torch, peak)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
+    ref_hash = committed_mask_hash() if size == 512 else None
     out = {
         "metric": METRIC, "value": result["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": result["ms_per_step"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "BASELINE config 3: %d^3 fp32 two-blob volume, regional_probability_map (alpha 0.1) + "
-                               "boundary_difference_exponential (sigma = RMS neighbour difference %.4f), fg balls / bg shell"
-                               % (size, vol["sigma"]),
-                   "shape": list(shape), "state_dtype": "float64", "parallelism": "zslab%d" % world if world > 1 else "single",
+        "config": {"workload": workload_text(size), "shape": list(shape), "state_dtype": "float64",
+                   "parallelism": "zslab%d" % world if world > 1 else "single", "sigma": vol["sigma"],
                    "l2": "inputs (%.1f GB) and solver state (%.1f GB) exceed the 126 MB L2; no flush needed"
-                         % (n * 10 / 1e9, n * 76 / 1e9),
+                         % (n * 10 / 1e9, n * 70 / 1e9),
                    "energy": result.get("energy"), "fg_voxels": result.get("fg_voxels"),
+                   "mask_sha256": result.get("mask_sha256"), "reference_mask_sha256": ref_hash,
+                   "mask_matches_reference": (result.get("mask_sha256") == ref_hash) if ref_hash else None,
                    "push_sweeps_per_step": result.get("push_sweeps"), "global_relabels_per_step": result.get("global_relabels"),
                    "relabel_sweeps_per_step": result.get("relabel_sweeps"),
                    "hbm_read_roofline_frac": (n * B_ALG / (result["ms_per_step"] * 1e-3)) / (peak * 1e9 * world),
-                   "hbm_read_roofline_note": "N*%d B / t_step / (%s peak %.0f GB/s * n_gpus), SURVEY.md §8d" % (B_ALG, peak_kind, peak)},
+                   "hbm_read_roofline_note": "N*%d B / t_step / (%s peak %.0f GB/s * n_gpus), SURVEY.md §8d" % (B_ALG, peak_kind, peak),
+                   "extra": extras},
         "clocks": result["clocks"],
         "e2e": result["e2e"],
         "gpu_launches": result["gpu_launches"],
         "roofline": result["roofline"],
+        "roofline_maxflow": result["roofline_maxflow"],
     }
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(args.cpu_size)
-        out["cpu_baseline"] = cpu_baseline_obj(r, args.cpu_size)
+        csize = args.cpu_size if args.cpu_size else 256
+        r = cpu_reference_run(csize)
+        out["cpu_baseline"] = cpu_baseline_obj(r, csize, size)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
-def roofline_from_stats(stats_list, n, peak, peak_kind):
-    """Roofline of the dominant kernel (by device time in the timed region).  Algorithmic bytes per launch:
-      k_boundary  (n-link stencil)   : image 4 B read + six float64 capacities 48 B written      = 52 B/voxel
-      k_init_tile (solver state)     : 6 caps + tr read (56 B), excess/sink/label/rmask written (21 B) = 77 B/voxel
-      k_push_tile (push pass)        : every voxel's excess + label must be inspected             = 12 B/voxel (dense bound)
-      k_relabel_tile (relabel pass)  : residual mask + label                                      =  5 B/voxel (dense bound)
-    """
-    k = len(stats_list)
-    cand = [
-        ("k_boundary (n-link stencil, K1)", 52, sum(s["ms_boundary"] for s in stats_list), k),
-        ("k_init_tile (solver state init)", 77, sum(s.get("ms_init", 0.0) for s in stats_list), k),
-        ("k_push_tile (two-colour push pass)", 12, sum(s["ms_push"] for s in stats_list), sum(s["push_sweeps"] for s in stats_list)),
-        ("k_relabel_tile (global relabel)", 5, sum(s["ms_relabel"] for s in stats_list), sum(s["global_relabels"] for s in stats_list)),
-    ]
-    name, bpv, ms, cnt = max(cand, key=lambda c: c[2])
-    cnt = max(cnt, 1)
-    # DRAM bytes of that kernel from the committed ncu --set full capture of this workload (profiles/), per launch
-    traffic = None
-    try:
-        if n == 512 ** 3:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_512cubed.json")))["bytes_per_launch"]
-            key = {"k_boundary": "k_boundary", "k_init_tile": "k_init_tile", "k_push_tile": "k_push_tile_tma",
-                   "k_relabel_tile": "k_bfs_coop"}[name.split(" ")[0]]
-            traffic = tj.get(key)
-    except Exception:
-        traffic = None
-    avg = ms / cnt
-    achieved = n * bpv / (avg * 1e-3) / 1e9 if avg > 0 else 0.0
-    return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "peak_kind": peak_kind, "launches": cnt, "avg_launch_ms": avg,
-            "algorithmic_bytes_per_launch": n * bpv,
-            "share_of_step": {c[0].split(" ")[0] + "_ms": c[2] for c in cand} | {
-                "solve_ms": sum(s["ms_solve"] for s in stats_list), "terms_ms": sum(s["ms_terms"] for s in stats_list),
-                "readout_ms": sum(s["ms_readout"] for s in stats_list)}}
-
-
-def bench_single(vol, args, torch):
-    import medpy_b200.graphcut as gc
+def resident_run(torch, vol, boundary, regional, steps, warmup):
+    """One BASELINE configuration with its inputs resident in HBM: `warmup` untimed + `steps` timed passes (CUDA events).
+    Returns (ms per step, energy, mask tensor, per-step stats)."""
     from medpy_b200.graphcut.device import graph_from_device_arrays
-    shape = vol["shape"]
-    n = int(numpy.prod(shape))
-    peak, peak_kind = measured_peak()
     stream = torch.cuda.current_stream()
-
-    # ---- inputs resident in HBM ----
     d_img = torch.from_numpy(vol["image"]).cuda()
-    d_prob = torch.from_numpy(vol["prob"]).cuda()
+    d_prob = torch.from_numpy(vol["prob"]).cuda() if regional else None
     d_fg = torch.from_numpy(vol["fg"].view(numpy.uint8)).cuda()
     d_bg = torch.from_numpy(vol["bg"].view(numpy.uint8)).cuda()
-    d_mask = torch.empty(shape, dtype=torch.uint8, device="cuda")
+    d_mask = torch.empty(vol["image"].shape, dtype=torch.uint8, device="cuda")
     graph = None
     stats = []
 
     def step(record):
         nonlocal graph
-        graph = graph_from_device_arrays(d_fg, d_bg, image=d_img, boundary="difference_exponential", sigma=vol["sigma"],
-                                         prob=d_prob, alpha=vol["alpha"], graph=graph, stream=stream.cuda_stream)
+        graph = graph_from_device_arrays(d_fg, d_bg, image=d_img, boundary=boundary, sigma=vol["sigma"],
+                                         prob=d_prob, alpha=vol.get("alpha"), graph=graph, stream=stream.cuda_stream)
         e = graph.maxflow()
         graph._nat().get_mask_into(d_mask.data_ptr())
         if record:
             stats.append(graph.stats())
         return e
 
-    sampler = ClockSampler(torch.cuda.current_device())
-    sampler.start()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step(False)
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
     ev0.record(stream)
     energy = None
-    for _ in range(args.steps):
+    for _ in range(steps):
         energy = step(True)
     ev1.record(stream)
     torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
+    return ev0.elapsed_time(ev1) / steps, energy, d_mask, stats
+
+
+def run_extras_single(torch, peak):
+    """BASELINE configs 2, 4 and 5 (on one GPU: the oracle of the 8-GPU run), each once, outside the headline's timed region."""
+    from medpy_b200 import synthetic
+    out = {}
+    todo = [("config2_256cubed_difference_exponential", (256, 256, 256), "difference_exponential", False),
+            ("config4_256x256x128x4_maximum_exponential", (256, 256, 128, 4), "maximum_exponential", True),
+            ("config5_1024cubed_single_gpu", (1024, 1024, 1024), "difference_exponential", False)]
+    for name, shape, boundary, fourd in todo:
+        try:
+            t0 = time.time()
+            vol = synthetic.multispectral_volume(shape, seed=0) if fourd else synthetic.two_blob_volume(shape, seed=0, with_prob=False)
+            gen_s = time.time() - t0
+            big = int(numpy.prod(shape)) >= 2 ** 29
+            ms, energy, d_mask, stats = resident_run(torch, vol, boundary, False, steps=2, warmup=1)
+            n = int(numpy.prod(shape))
+            st = stats[-1]
+            mask = d_mask.cpu().numpy()
+            out[name] = {"shape": list(shape), "value": n / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms, "steps": 2, "warmup": 1,
+                         "energy": energy, "fg_voxels": int(mask.sum(dtype=numpy.int64)), "mask_sha256": sha256_of(mask),
+                         "hbm_read_roofline_frac": (n * 7 / (ms * 1e-3)) / (peak * 1e9),
+                         "push_sweeps": st["push_sweeps"], "global_relabels": st["global_relabels"], "relabel_sweeps": st["relabel_sweeps"],
+                         "ms_build": st["ms_boundary"], "ms_relabel": st["ms_relabel"], "ms_push": st["ms_push"], "ms_solve": st["ms_solve"],
+                         "gen_s": gen_s, "sigma": vol["sigma"]}
+            del d_mask, mask, vol
+            torch.cuda.empty_cache()
+            if big:
+                import gc as _gc
+                _gc.collect()
+        except Exception as exc:      # an extra must never take the headline line down with it
+            out[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            torch.cuda.empty_cache()
+    return out
+
+
+def bench_single(vol, args, torch):
+    import medpy_b200.graphcut as gc
+    shape = vol["shape"]
+    n = int(numpy.prod(shape))
+    peak, peak_kind = measured_peak()
+
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    ms, energy, d_mask, stats = resident_run(torch, vol, "difference_exponential", True, steps=args.steps, warmup=args.warmup)
     clocks = sampler.stop()
-    fg_vox = int(d_mask.sum().item())
-    value = n * args.steps / (ms * 1e-3) / 1e6
+    mask_host = d_mask.cpu().numpy()
+    fg_vox = int(mask_host.sum(dtype=numpy.int64))
+    mask_hash = sha256_of(mask_host)
+    del d_mask, mask_host
+    value = n / (ms * 1e-3) / 1e6
     launches = int(sum(s["kernel_launches"] for s in stats))
-    roof = roofline_from_stats(stats, n, peak, peak_kind)
+    roof, roof_mf = rooflines(stats, n, n, peak, peak_kind)
+    torch.cuda.empty_cache()
 
     # ---- end to end through the public API from pinned host buffers ----
     def pin(a):
@@ -346,8 +446,6 @@ def bench_single(vol, args, torch):
     h_img, h_prob, h_fg, h_bg = (k[1] for k in keep)
     h_fg = h_fg.view(numpy.bool_)
     h_bg = h_bg.view(numpy.bool_)
-    del graph, d_img, d_prob, d_fg, d_bg, d_mask
-    torch.cuda.empty_cache()
 
     def e2e_step():
         g = gc.graph_from_voxels(h_fg, h_bg, regional_term=gc.energy_voxel.regional_probability_map,
@@ -371,10 +469,12 @@ def bench_single(vol, args, torch):
     dt = time.perf_counter() - t0
     e2e = {"value": n * args.steps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(n * 10), "d2h_bytes_per_step": int(n + 8),
            "ms_per_step": 1e3 * dt / args.steps, "api": "medpy_b200.graphcut.graph_from_voxels -> maxflow -> get_mask",
-           "energy_matches_resident_run": bool(e_e2e == energy), "timer": "host perf_counter around synchronised steps "
-           "(H2D staging and the D2H mask copy are synchronous host calls inside)"}
-    return {"value": value, "ms_per_step": ms / args.steps, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-            "roofline": roof, "energy": energy, "fg_voxels": fg_vox,
+           "energy_matches_resident_run": bool(abs(e_e2e - energy) <= 1e-12 * abs(energy)),
+           "mask_matches_resident_run": bool(sha256_of(m_e2e) == mask_hash),
+           "timer": "host perf_counter around synchronised steps (the z-chunked H2D uploads and the D2H mask copy are inside)"}
+    del m_e2e, keep
+    return {"value": value, "ms_per_step": ms, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roof, "roofline_maxflow": roof_mf, "energy": energy, "fg_voxels": fg_vox, "mask_sha256": mask_hash,
             "push_sweeps": stats[-1]["push_sweeps"], "global_relabels": stats[-1]["global_relabels"],
             "relabel_sweeps": stats[-1]["relabel_sweeps"]}
 
@@ -386,8 +486,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=int(os.environ.get("MEDPY_BENCH_SIZE", "512")))
-    ap.add_argument("--cpu-size", type=int, default=int(os.environ.get("MEDPY_BENCH_CPU_SIZE", "256")))
+    ap.add_argument("--cpu-size", type=int, default=int(os.environ.get("MEDPY_BENCH_CPU_SIZE", "0")),
+                    help="edge of the CPU arm's volume; 0 = the workload's own size for --impl reference, 256 for the cpu_baseline object")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip config.extra (configs 2, 4, 5)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

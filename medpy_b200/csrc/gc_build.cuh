@@ -111,7 +111,7 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
     const int gy = y0 + ly, gx = x0 + lx;
     const bool col_in = gy < L.dim[1] && gx < L.dim[2];
     const bool has_py = gy + 1 < L.dim[1], has_px = gx + 1 < L.dim[2];
-    const double inv_sp_z = spacing ? P.spacing[0] : 1.0, inv_sp_y = spacing ? P.spacing[1] : 1.0, inv_sp_x = spacing ? P.spacing[2] : 1.0;
+    const double sp_z = spacing ? P.spacing[0] : 1.0, sp_y = spacing ? P.spacing[1] : 1.0, sp_x = spacing ? P.spacing[2] : 1.0;
     auto at = [&](int hz, int hy, int hx) -> E { return s_img[(hz * BUILD_HY + hy) * BUILD_BX + hx]; };
 
     int isbad = 0;
@@ -122,7 +122,7 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
     if (col_in && z0 > 0 && z0 < L.dim[0]) {
         const double a = build_val<E>(at(0, ly + 1, lx + 1), use_max);
         double w = build_pair<FN, E>(P, a, at(1, ly + 1, lx + 1), use_max);
-        if (spacing) w = __ddiv_rn(w, inv_sp_z);
+        if (spacing) w = __ddiv_rn(w, sp_z);
         if (w <= 0.0) isbad = 1;
         wz_back = w;
     }
@@ -137,9 +137,9 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
         if (gz < L.dim[0]) {
             if (pin) {
                 const double a = build_val<E>(at(hz, ly + 1, lx + 1), use_max);
-                if (gz + 1 < L.dim[0]) { wz = build_pair<FN, E>(P, a, at(hz + 1, ly + 1, lx + 1), use_max); if (spacing) wz = __ddiv_rn(wz, inv_sp_z); if (wz <= 0.0) isbad = 1; }
-                if (has_py) { wy = build_pair<FN, E>(P, a, at(hz, ly + 2, lx + 1), use_max); if (spacing) wy = __ddiv_rn(wy, inv_sp_y); if (wy <= 0.0) isbad = 1; }
-                if (has_px) { wx = build_pair<FN, E>(P, a, at(hz, ly + 1, lx + 2), use_max); if (spacing) wx = __ddiv_rn(wx, inv_sp_x); if (wx <= 0.0) isbad = 1; }
+                if (gz + 1 < L.dim[0]) { wz = build_pair<FN, E>(P, a, at(hz + 1, ly + 1, lx + 1), use_max); if (spacing) wz = __ddiv_rn(wz, sp_z); if (wz <= 0.0) isbad = 1; }
+                if (has_py) { wy = build_pair<FN, E>(P, a, at(hz, ly + 2, lx + 1), use_max); if (spacing) wy = __ddiv_rn(wy, sp_y); if (wy <= 0.0) isbad = 1; }
+                if (has_px) { wx = build_pair<FN, E>(P, a, at(hz, ly + 1, lx + 2), use_max); if (spacing) wx = __ddiv_rn(wx, sp_x); if (wx <= 0.0) isbad = 1; }
             }
             wyb[(ly + 1) * 32 + lx] = wy;
             wxb[ly * 33 + lx + 1] = wx;
@@ -149,7 +149,7 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
                 if (y0 > 0 && gx < L.dim[2]) {
                     const double a = build_val<E>(at(hz, 0, lx + 1), use_max);
                     w = build_pair<FN, E>(P, a, at(hz, 1, lx + 1), use_max);
-                    if (spacing) w = __ddiv_rn(w, inv_sp_y);
+                    if (spacing) w = __ddiv_rn(w, sp_y);
                     if (w <= 0.0) isbad = 1;
                 }
                 wyb[lx] = w;
@@ -158,7 +158,7 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
                 if (x0 > 0 && y0 + lx < L.dim[1]) {
                     const double a = build_val<E>(at(hz, lx + 1, 0), use_max);
                     w = build_pair<FN, E>(P, a, at(hz, lx + 1, 1), use_max);
-                    if (spacing) w = __ddiv_rn(w, inv_sp_x);
+                    if (spacing) w = __ddiv_rn(w, sp_x);
                     if (w <= 0.0) isbad = 1;
                 }
                 wxb[lx * 33] = w;
@@ -241,7 +241,7 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
         double t = s_red[0];
 #pragma unroll
         for (int w = 1; w < 8; ++w) t = __dadd_rn(t, s_red[w]);
-        partials[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = t;
+        partials[((A.z_tile0 + blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = t;
     }
     if (tid < 4) {
         const int tx = (x0 >> 3) + tid, ty = y0 >> 3, tz = z0 >> 3;

@@ -101,6 +101,15 @@ class SlabSolver:
     def add_markers(self, fg_local, bg_local):
         self.handle.add_markers(fg_local, bg_local)
 
+    def build(self, fg_local, bg_local, image_local=None, kind=None, sigma=None, spacing=False, prob_local=None, alpha=None,
+              norm=math.nan, compute_f32=True):
+        """Everything graph_from_voxels adds (regional term, boundary term, fg / bg markers) in one native call: the
+        fused single-pass build of the slab (mgc_build_voxel_graph)."""
+        k = -1 if kind is None else (KINDS[kind] if isinstance(kind, str) else int(kind))
+        sp = [float(s) for s in spacing] if spacing else None
+        self.handle.build_voxel_graph(prob_local, 0.0 if alpha is None else float(alpha), bool(compute_f32) and prob_local is not None,
+                                      k, image_local, 0.0 if sigma is None else float(sigma), sp, float(norm), fg_local, bg_local)
+
     # ---------------------------------------------------------------------------------------------- messages
     def _views(self, buf):
         h = buf[: self.plane * 4].view(self.torch.int32)
@@ -169,6 +178,7 @@ class SlabSolver:
 
     def solve(self, max_rounds=100000):
         """Run to a maximum preflow.  Returns this rank's energy share; use ``energy()`` for the total."""
+        self.stats = {"exchanges": 0, "relabel_rounds": 0, "global_relabels": 0, "push_passes": 0}   # per solve
         self.handle.slab_begin()
         passes = self.passes0
         rounds = 0
@@ -206,13 +216,12 @@ def graphcut_slab(fg_markers, bg_markers, image=None, boundary=None, sigma=None,
     import torch.distributed as dist
     shape = tuple(fg_markers.shape)
     s = SlabSolver(shape, group=group, handle_factory=handle_factory)
-    if prob is not None:
-        s.add_regional_probability(s.local_slice(prob), alpha, "float32" in str(prob.dtype))
-    if boundary is not None:
-        if boundary.endswith("linear") and (isinstance(norm, float) and math.isnan(norm)):
-            raise ValueError("linear boundary terms need the GLOBAL normaliser `norm` in slab mode")
-        s.add_boundary(boundary, s.local_slice(image), sigma, spacing, norm)
-    s.add_markers(s.local_slice(fg_markers), s.local_slice(bg_markers))
+    if boundary is not None and boundary.endswith("linear") and (isinstance(norm, float) and math.isnan(norm)):
+        raise ValueError("linear boundary terms need the GLOBAL normaliser `norm` in slab mode")
+    s.build(s.local_slice(fg_markers), s.local_slice(bg_markers),
+            image_local=s.local_slice(image) if boundary is not None else None, kind=boundary, sigma=sigma, spacing=spacing,
+            prob_local=s.local_slice(prob) if prob is not None else None, alpha=alpha, norm=norm,
+            compute_f32=prob is not None and "float32" in str(prob.dtype))
     s.solve()
     energy = s.energy()
     own = s.mask()
@@ -233,7 +242,7 @@ def graphcut_slab(fg_markers, bg_markers, image=None, boundary=None, sigma=None,
 # ------------------------------------------------------------------------------------------------------
 # bench support (bench.py --gpus N, launched with torchrun)
 # ------------------------------------------------------------------------------------------------------
-def slab_volume(shape, rank, world, seed=0):
+def slab_volume(shape, rank, world, seed=0, with_prob=True):
     """This rank's planes (+ ghost planes) of the synthetic two-blob workload and the GLOBAL sigma: every rank
     generates only what it needs (the generator seeds each plane separately) and the per-plane partial sums of the
     RMS neighbour difference are all-gathered and added with fsum, so sigma is bit-identical to the single-process
@@ -244,7 +253,7 @@ def slab_volume(shape, rank, world, seed=0):
     z0, z1 = slab_bounds(shape[0], world, rank)
     a = z0 - (1 if z0 > 0 else 0)
     b = z1 + (1 if z1 < shape[0] else 0)
-    vol = synthetic.two_blob_volume(shape, seed=seed, planes=(a, b))
+    vol = synthetic.two_blob_volume(shape, seed=seed, planes=(a, b), with_prob=with_prob)
     own = vol["image"][z0 - a: z0 - a + (z1 - z0)]
     nxt = vol["image"][z1 - a] if z1 < shape[0] else None
     parts = synthetic.neighbour_difference_partials(own, next_plane=nxt)
@@ -263,39 +272,47 @@ def slab_volume(shape, rank, world, seed=0):
     return vol
 
 
-def bench_slab(shape, args, rank, world, local_rank):
-    """Strong-scaling run of bench.py's workload: the volume is partitioned once, the slab inputs stay resident
-    in HBM, each timed step rebuilds the terms, solves and extracts the mask.  Returns the dict bench.py prints
-    (meaningful on rank 0)."""
-    import time
+def gather_mask(s, d_mask_own, shape):
+    """Full uint8 mask on rank 0 (None elsewhere): the owned planes of every rank, gathered over NCCL."""
     import torch
     import torch.distributed as dist
-    from bench import ClockSampler, measured_peak, UNIT  # noqa
+    counts = [slab_bounds(shape[0], s.world, r) for r in range(s.world)]
+    pmax = max(b - a for a, b in counts)
+    pad = torch.zeros((pmax,) + tuple(shape[1:]), dtype=torch.uint8, device=d_mask_own.device)
+    pad[: d_mask_own.shape[0]] = d_mask_own
+    parts = [torch.empty_like(pad) for _ in range(s.world)] if s.rank == 0 else None
+    dist.gather(pad, parts, dst=0)
+    if s.rank != 0:
+        return None
+    return numpy.concatenate([p[: b - a].cpu().numpy() for p, (a, b) in zip(parts, counts)], axis=0)
+
+
+def _slab_resident(shape, rank, world, local_rank, regional, steps, warmup, sampler=None):
+    """z-slab run with the slab inputs resident in HBM: every timed step rebuilds the graph (fused build), solves and
+    extracts the mask.  Timing: CUDA events between barriers, max over ranks."""
+    import torch
+    import torch.distributed as dist
     dev = torch.device("cuda", local_rank)
-    n = int(numpy.prod(shape))
-    vol = slab_volume(shape, rank, world)
+    vol = slab_volume(shape, rank, world, with_prob=regional)
     s = SlabSolver(shape, rank=rank, world=world, device=local_rank)
-    s.local_slice = lambda arr: arr          # the arrays already are this rank's planes
     d_img = torch.from_numpy(numpy.ascontiguousarray(vol["image"])).to(dev)
-    d_prob = torch.from_numpy(numpy.ascontiguousarray(vol["prob"])).to(dev)
+    d_prob = torch.from_numpy(numpy.ascontiguousarray(vol["prob"])).to(dev) if regional else None
     d_fg = torch.from_numpy(numpy.ascontiguousarray(vol["fg"]).view(numpy.uint8)).to(dev)
     d_bg = torch.from_numpy(numpy.ascontiguousarray(vol["bg"]).view(numpy.uint8)).to(dev)
     d_mask = torch.empty((s.z1 - s.z0,) + tuple(shape[1:]), dtype=torch.uint8, device=dev)
-    launches = []
+    launches, build_ms = [], []
 
     def step():
         s.reset()
-        s.add_regional_probability(d_prob, vol["alpha"], True)
-        s.add_boundary("difference_exponential", d_img, vol["sigma"], False)
-        s.add_markers(d_fg, d_bg)
+        s.build(d_fg, d_bg, image_local=d_img, kind="difference_exponential", sigma=vol["sigma"], prob_local=d_prob,
+                alpha=vol.get("alpha"))
         s.solve()
         s.handle.get_mask_into(d_mask.data_ptr())
         return s.energy()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if sampler is not None and rank == 0:
         sampler.start()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     torch.cuda.synchronize()
     dist.barrier()
@@ -305,36 +322,54 @@ def bench_slab(shape, args, rank, world, local_rank):
     dist.barrier()
     ev0.record(stream)
     energy = None
-    for _ in range(args.steps):
+    for _ in range(steps):
         energy = step()
-        launches.append(s.handle.stats()["kernel_launches"])
+        st = s.handle.stats()
+        launches.append(st["kernel_launches"])
+        build_ms.append(st["ms_boundary"])
     ev1.record(stream)
     torch.cuda.synchronize()
     dist.barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
-    clocks = sampler.stop() if rank == 0 else None
+    ms = float(ms.item()) / steps
+    clocks = sampler.stop() if (sampler is not None and rank == 0) else None
     fgv = torch.tensor([int(d_mask.sum().item())], dtype=torch.int64, device=dev)
     dist.all_reduce(fgv)
     nl = torch.tensor([int(sum(launches))], dtype=torch.int64, device=dev)
     dist.all_reduce(nl)
-    st = s.handle.stats()
+    full = gather_mask(s, d_mask, shape)
+    return dict(s=s, vol=vol, ms=ms, energy=energy, clocks=clocks, fg_voxels=int(fgv.item()), launches=int(nl.item()),
+                build_ms=build_ms, mask=full, d_mask=d_mask)
+
+
+def bench_slab(shape, args, rank, world, local_rank):
+    """Strong-scaling run of bench.py's workload: the volume is partitioned once, the slab inputs stay resident
+    in HBM, each timed step rebuilds the graph, solves and extracts the mask.  Returns the dict bench.py prints
+    (meaningful on rank 0)."""
+    import time
+    import torch
+    import torch.distributed as dist
+    from bench import ClockSampler, measured_peak, rooflines, sha256_of, UNIT  # noqa
+    dev = torch.device("cuda", local_rank)
+    n = int(numpy.prod(shape))
+    r = _slab_resident(shape, rank, world, local_rank, True, args.steps, args.warmup, sampler=ClockSampler(local_rank))
+    s, vol, ms, energy = r["s"], r["vol"], r["ms"], r["energy"]
+    mask_hash = sha256_of(r["mask"]) if rank == 0 else None
     peak, peak_kind = measured_peak()
+    del r["d_mask"]
+    torch.cuda.empty_cache()
 
     # ---- end to end: pinned host slabs -> device -> solve -> host mask ----
     def pin(a):
         t = torch.from_numpy(numpy.ascontiguousarray(a)).pin_memory()
         return t, t.numpy()
-    keep = [pin(s.local_slice(vol["image"])), pin(s.local_slice(vol["prob"])),
-            pin(s.local_slice(vol["fg"]).view(numpy.uint8)), pin(s.local_slice(vol["bg"]).view(numpy.uint8))]
+    keep = [pin(vol["image"]), pin(vol["prob"]), pin(vol["fg"].view(numpy.uint8)), pin(vol["bg"].view(numpy.uint8))]
     h_img, h_prob, h_fg, h_bg = (k[1] for k in keep)
 
     def e2e_step():
         s.reset()
-        s.add_regional_probability(h_prob, vol["alpha"], True)
-        s.add_boundary("difference_exponential", h_img, vol["sigma"], False)
-        s.add_markers(h_fg, h_bg)
+        s.build(h_fg, h_bg, image_local=h_img, kind="difference_exponential", sigma=vol["sigma"], prob_local=h_prob, alpha=vol["alpha"])
         s.solve()
         m = s.mask()
         return s.energy(), m
@@ -354,20 +389,40 @@ def bench_slab(shape, args, rank, world, local_rank):
     local_bytes = int(numpy.prod(h_img.shape)) * 10
     e2e = {"value": n * args.steps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(n * 10 + (world - 1) * 2 * s.plane * 10),
            "d2h_bytes_per_step": int(n + 8 * world), "ms_per_step": 1e3 * dt / args.steps,
-           "api": "medpy_b200.distributed.SlabSolver (reset/add_*/solve/mask) per rank", "energy_matches_resident_run": bool(e_e2e == energy),
+           "api": "medpy_b200.distributed.SlabSolver (reset/build/solve/mask) per rank", "energy_matches_resident_run": bool(e_e2e == energy),
            "timer": "host perf_counter between barriers, max over ranks", "rank0_h2d_bytes": local_bytes}
-    # roofline of the dominant kernel on rank 0 (K1, the n-link stencil: per-rank algorithmic bytes = local voxels x 52 B,
-    # duration from the library's CUDA events around the last timed step's launch)
+    # same kernel choice as at N = 1: the fused build, here on rank 0's slab (library CUDA events around each launch)
     n_local = int(numpy.prod(vol["image"].shape))
-    kb_ms = st["ms_boundary"]
-    achieved = n_local * 52 / (kb_ms * 1e-3) / 1e9 if kb_ms > 0 else None
-    roof = {"bound": "hbm", "kernel": "k_boundary (n-link stencil, K1) on rank 0's slab", "achieved": achieved,
-            "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_kind": peak_kind,
-            "launches": 1, "avg_launch_ms": kb_ms, "algorithmic_bytes_per_launch": n_local * 52,
-            "share_of_step": {"k_boundary_ms": kb_ms, "k_init_tile_ms": st.get("ms_init", 0.0), "terms_ms_cumulative": st["ms_terms"],
-                              "exchanges_cumulative": s.stats["exchanges"],
-                              "note": "slab stepping is asynchronous: push/relabel kernels are not timed individually at N > 1"}}
-    return {"value": n * args.steps / (ms * 1e-3) / 1e6, "ms_per_step": ms / args.steps, "clocks": clocks, "e2e": e2e,
-            "gpu_launches": int(nl.item()), "roofline": roof, "energy": energy, "fg_voxels": int(fgv.item()),
+    stats_like = [{"ms_boundary": b, "ms_relabel": 0.0, "ms_push": 0.0, "ms_solve": 0.0, "ms_readout": 0.0} for b in r["build_ms"]]
+    roof, roof_mf = rooflines(stats_like, n_local, n, peak, peak_kind)
+    roof["kernel"] += " on rank 0's slab"
+    roof["share_of_step"] = {"k_build_tile_ms": roof["avg_launch_ms"], "step_ms": ms, "exchanges_cumulative": s.stats["exchanges"],
+                             "note": "slab stepping is asynchronous: push / relabel kernels are not timed individually at N > 1"}
+    roof_mf["ms_per_step"] = None
+    return {"value": n / (ms * 1e-3) / 1e6, "ms_per_step": ms, "clocks": r["clocks"], "e2e": e2e,
+            "gpu_launches": r["launches"], "roofline": roof, "roofline_maxflow": roof_mf, "energy": energy, "fg_voxels": r["fg_voxels"],
+            "mask_sha256": mask_hash,
             "push_sweeps": s.stats["push_passes"], "global_relabels": s.stats["global_relabels"],
             "relabel_sweeps": s.stats["relabel_rounds"], "sigma": vol["sigma"]}
+
+
+def bench_config5(args, rank, world, local_rank, shape=(1024, 1024, 1024)):
+    """BASELINE config 5: 1024^3 fp32, boundary_difference_exponential, z-slab partitioned over the ranks.  One warm-up
+    and two timed steps; the gathered mask is hashed on rank 0 (compare with the single-GPU run's config.extra)."""
+    import torch
+    from bench import measured_peak, sha256_of, UNIT  # noqa
+    try:
+        r = _slab_resident(shape, rank, world, local_rank, False, 2, 1)
+    except Exception as exc:
+        return {"error": "%s: %s" % (type(exc).__name__, exc)}
+    n = int(numpy.prod(shape))
+    peak, _ = measured_peak()
+    s = r["s"]
+    out = {"shape": list(shape), "value": n / (r["ms"] * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": r["ms"], "steps": 2, "warmup": 1,
+           "energy": r["energy"], "fg_voxels": r["fg_voxels"], "mask_sha256": sha256_of(r["mask"]) if rank == 0 else None,
+           "hbm_read_roofline_frac": (n * 7 / (r["ms"] * 1e-3)) / (peak * 1e9 * world), "n_gpus": world,
+           "push_passes": s.stats["push_passes"], "global_relabels": s.stats["global_relabels"], "exchanges": s.stats["exchanges"],
+           "sigma": r["vol"]["sigma"]}
+    del r
+    torch.cuda.empty_cache()
+    return out

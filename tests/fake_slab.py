@@ -66,6 +66,14 @@ class FakeSlab:
         if bg is not None:
             self._tw(0.0, 65535.0, where=self._np(bg).astype(bool).ravel())
 
+    def build_voxel_graph(self, prob, alpha, compute_f32, kind, image, sigma, spacing, norm, fg, bg):
+        """mgc_build_voxel_graph: regional term, boundary term, markers, in the reference's order."""
+        if prob is not None:
+            self.add_regional_probability(prob, alpha, compute_f32)
+        if kind >= 0:
+            self.add_boundary(kind, image, sigma, spacing, norm)
+        self.add_markers(fg, bg)
+
     # ---- stepping ------------------------------------------------------------------------------------------
     def slab_plane_elems(self):
         return int(numpy.prod(self.shape[1:]))
