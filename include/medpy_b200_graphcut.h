@@ -187,6 +187,11 @@ typedef struct mgc_voxel_terms {
     const uint32_t* fg_bits; /* bit-packed marker volumes or NULL */
     const uint32_t* bg_bits;
     int32_t bits_mem;        /* MGC_MEM_HOST / MGC_MEM_DEVICE of fg_bits / bg_bits */
+    /* Optional (host bit planes only): the number of leading 32-bit WORDS of BOTH planes that have been written so far,
+     * advanced by a producer thread while this call runs (the binding packs the marker bytes on worker threads while the
+     * image is already on its way to the device).  The call waits for it before it enqueues the upload of a chunk.
+     * NULL: the planes are complete. */
+    const volatile int64_t* bits_ready_words;
 } mgc_voxel_terms;
 int mgc_build_voxel_graph(mgc_graph* g, const mgc_voxel_terms* terms);
 /* 1 if mgc_build_voxel_graph would take the single-pass path on a fresh state of this handle. */
@@ -248,6 +253,23 @@ int mgc_slab_count_active_dev(mgc_graph* g, unsigned long long* count_dev);
 /* Finish: build the mask of the owned planes and this slab's share of the energy
  * (flow absorbed by the owned sink links + owned add_tweights constants). */
 int mgc_slab_finish(mgc_graph* g, double* energy_part);
+
+/* ---- z-slab solve inside the library (NCCL over NVLink on the handle's stream) ------------------------------ */
+
+/* The stepping calls above let a host drive the slabs; these three run the WHOLE distributed solve natively: border
+ * messages go out with ncclSend / ncclRecv (grouped, on the handle's stream), the stop test is one ncclAllReduce and
+ * one host synchronisation per relabel round, the energy is all-reduced (float64).  libnccl.so.2 is bound at run time
+ * (the copy already loaded in the process, e.g. torch's); asynchronous NCCL errors are polled at every host decision
+ * and returned as MGC_E_CUDA instead of hanging.
+ *   mgc_slab_comm_unique_id : 128-byte ncclUniqueId made by ONE rank; the host distributes it (any transport);
+ *   mgc_slab_comm_init      : collective over the `world` slab ranks (rank r owns the r-th slab);
+ *   mgc_slab_solve          : collective; *energy_total = the global min-cut energy on every rank.  mgc_get_mask then
+ *                             returns the rank's owned planes. */
+int mgc_slab_comm_unique_id(void* out128);
+int mgc_slab_comm_init(mgc_graph* g, int32_t rank, int32_t world, const void* unique_id128);
+int mgc_slab_solve(mgc_graph* g, double* energy_total);
+int mgc_slab_solve_stats(const mgc_graph* g, int64_t* exchanges, int64_t* relabel_rounds, int64_t* push_passes,
+                         int64_t* global_relabels);
 
 /* ---- general sparse graphs ----------------------------------------------------- */
 

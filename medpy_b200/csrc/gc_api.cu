@@ -13,6 +13,11 @@
 #include "gc_build.cuh"
 #include "gc_gradient.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>
+#include <nvtx3/nvToolsExt.h>
+
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -148,6 +153,8 @@ struct mgc_graph {
     bool tr_fresh = true;              // same for tr[]
     bool state_init = false;
     bool flow_started = false;         // push kernels have run since the last reset: cap[] holds residuals, not the terms
+    bool debug_checks = false;         // MEDPY_GC_DEBUG=1: device-side invariant + flow-conservation checks around every solve
+    double debug_excess0 = 0.0;        // clamped source excess the solve started from
     bool fuse_build = true;            // mgc_build_voxel_graph uses the single-pass k_build_tile (MEDPY_GC_FUSE=0: four passes)
     int build_chunks = 8;              // host inputs: z-chunks whose upload overlaps the build of the previous chunk
     bool solved = false;
@@ -191,11 +198,31 @@ struct mgc_graph {
     int relax_batch = 4;
     int64_t max_rounds = 100000;
 
+    // z-slab solve inside the library (mgc_slab_comm_init / mgc_slab_solve): NCCL communicator of the slab ranks, border
+    // message buffers [labels int32 | pad | flow float64] per neighbour and direction, stop-test scalars
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    char* msg[4] = {nullptr, nullptr, nullptr, nullptr};   // send_lo, send_hi, recv_lo, recv_hi (device)
+    size_t msg_h_bytes = 0, msg_bytes = 0;
+    long long* d_stat = nullptr;       // [changed in round A, changed in round B, active voxels] (device, all-reduced in place)
+    long long* h_stat = nullptr;       // pinned mirror
+    double* d_esum = nullptr;          // energy all-reduce
+    int64_t slab_exchanges = 0, slab_relabel_rounds = 0, slab_push_passes = 0, slab_global_relabels = 0;
+
     mgc_stats st{};
     std::string err;
 };
 
 namespace {
+
+void slab_comm_release(mgc_graph* g);
+
+// NVTX range per phase (build / relabel / push / readout / exchange): visible in nsys / ncu timelines, a no-op without a
+// profiler attached
+struct Nvtx {
+    explicit Nvtx(const char* name) { nvtxRangePushA(name); }
+    ~Nvtx() { nvtxRangePop(); }
+};
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -594,6 +621,7 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
     for (auto& ev : g->ev_slot) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto& ev : g->ev_chunk) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto& ev : g->ev_terms) cudaEventCreate(&ev);
+    if (const char* f0 = getenv("MEDPY_GC_DEBUG")) g->debug_checks = atoi(f0) != 0;
     if (const char* f1 = getenv("MEDPY_GC_FUSE")) g->fuse_build = atoi(f1) != 0;
     if (const char* f2 = getenv("MEDPY_GC_CHUNKS")) if (atoi(f2) > 0) g->build_chunks = atoi(f2);
     cudaEventCreateWithFlags(&g->ev_bad, cudaEventDisableTiming);
@@ -794,6 +822,7 @@ int read_tcount(mgc_graph* g, int idx, int* out)
 // first call: solver state + first labels + first worklists in one pass (k_init_tile)
 int init_tiles(mgc_graph* g)
 {
+    Nvtx range("mgc:init_state");
     CK(cudaMemsetAsync(g->d_tcount, 0, 256, g->stream));
     g->pl_sel[0] = g->pl_sel[1] = 0;
     cudaEventRecord(g->ev[4], g->stream);
@@ -932,6 +961,7 @@ int relabel_tiles_run(mgc_graph* g, int* any, bool want_any = true)
 
 int relabel_tiles(mgc_graph* g)
 {
+    Nvtx range("mgc:global_relabel");
     cudaEventRecord(g->ev[2], g->stream);
     int rc = relabel_tiles_begin(g);
     if (rc) return rc;
@@ -971,6 +1001,7 @@ int push_color(mgc_graph* g, int color)
 
 int push_tiles(mgc_graph* g, int passes)
 {
+    Nvtx range("mgc:push_passes");
     cudaEventRecord(g->ev[2], g->stream);
     for (int p = 0; p < passes; ++p) {
         int rc = push_color(g, 0);
@@ -1039,6 +1070,37 @@ int solve_coop(mgc_graph* g, int flags, int passes, int64_t* active_out)
     return MGC_OK;
 }
 
+// MEDPY_GC_DEBUG=1: device-side invariants; `after` = compare flow conservation with the excess recorded before the solve
+int debug_invariants(mgc_graph* g, bool after)
+{
+    if (!g->debug_checks) return MGC_OK;
+    double* d = g->d_scalars + 4;        // [4] excess, [5] absorbed, [6] violations
+    CK(cudaMemsetAsync(d, 0, 3 * sizeof(double), g->stream));
+    const bool tiles3 = g->use_tiles && g->nd == 3;
+    if (g->nd == 3) {
+        if (tiles3) k_debug_invariants<3, double, true><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, d);
+        else        k_debug_invariants<3, double, false><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, d);
+    } else {
+        k_debug_invariants<4, double, false><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, d);
+    }
+    double h[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    if (h[2] != 0.0) {
+        g->err = "debug check: " + std::to_string((long long)h[2]) + " invariant violation(s) (negative capacity / excess, absorbed flow out of range or stale residual mask)";
+        return MGC_E_STATE;
+    }
+    if (!after) { g->debug_excess0 = h[0] + h[1]; return MGC_OK; }
+    const double scale = fabs(g->debug_excess0) > 1.0 ? fabs(g->debug_excess0) : 1.0;
+    if (!g->slab && !(fabs(h[0] + h[1] - g->debug_excess0) <= 1e-9 * scale)) {
+        char buf[200];
+        snprintf(buf, sizeof(buf), "debug check: flow not conserved: excess %.17g + absorbed %.17g != initial %.17g", h[0], h[1], g->debug_excess0);
+        g->err = buf;
+        return MGC_E_STATE;
+    }
+    return MGC_OK;
+}
+
 int solve_tiles(mgc_graph* g)
 {
     int rc = materialise_zeros(g);
@@ -1081,6 +1143,7 @@ int solve_tiles(mgc_graph* g)
 
 int readout(mgc_graph* g, double* energy_part)
 {
+    Nvtx range("mgc:readout");
     if (g->use_tiles && g->nd == 3) k_readout<double, true><<<rblocks(g), 256, 0, g->stream>>>(g->L, g->S, g->mask_dev, g->partials);
     else                            k_readout<double, false><<<rblocks(g), 256, 0, g->stream>>>(g->L, g->S, g->mask_dev, g->partials);
     CK(cudaMemsetAsync(g->d_scalars + 1, 0, sizeof(double), g->stream));
@@ -1097,6 +1160,107 @@ int readout(mgc_graph* g, double* energy_part)
         g->init_timed = false;
     }
     return MGC_OK;
+}
+
+// ---- NCCL, bound at run time ------------------------------------------------------------------------------
+// The library does not link libnccl: the first mgc_slab_comm_* call binds the copy that is already loaded in the
+// process (torch's, when the host side is Python) or opens libnccl.so.2 itself.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t*) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    bool ok = false;
+};
+
+NcclApi& nccl_api()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return;
+        bool all = true;
+        auto bind = [&](auto& fn, const char* name) { fn = reinterpret_cast<std::remove_reference_t<decltype(fn)>>(dlsym(h, name)); if (!fn) all = false; };
+        bind(api.GetUniqueId, "ncclGetUniqueId"); bind(api.CommInitRank, "ncclCommInitRank"); bind(api.CommDestroy, "ncclCommDestroy");
+        bind(api.CommAbort, "ncclCommAbort"); bind(api.CommGetAsyncError, "ncclCommGetAsyncError"); bind(api.GetErrorString, "ncclGetErrorString");
+        bind(api.AllReduce, "ncclAllReduce"); bind(api.Send, "ncclSend"); bind(api.Recv, "ncclRecv");
+        bind(api.GroupStart, "ncclGroupStart"); bind(api.GroupEnd, "ncclGroupEnd");
+        api.ok = all;
+    });
+    return api;
+}
+
+#define NK(call)                                                                                   \
+    do {                                                                                           \
+        ncclResult_t _r = (call);                                                                  \
+        if (_r != ncclSuccess) {                                                                   \
+            g->err = std::string(#call) + ": " + nccl_api().GetErrorString(_r);                    \
+            return MGC_E_CUDA;                                                                     \
+        }                                                                                          \
+    } while (0)
+
+void slab_comm_release(mgc_graph* g)
+{
+    if (g->comm && nccl_api().ok) nccl_api().CommDestroy(g->comm);
+    g->comm = nullptr;
+}
+
+// asynchronous NCCL errors (a peer that died, a network fault) surface here instead of as a hang: polled at every
+// host-visible decision of the slab solve
+int slab_comm_poll(mgc_graph* g)
+{
+    if (!g->comm) return MGC_OK;
+    ncclResult_t async = ncclSuccess;
+    NK(nccl_api().CommGetAsyncError(g->comm, &async));
+    if (async != ncclSuccess && async != ncclInProgress) {
+        g->err = std::string("NCCL asynchronous error: ") + nccl_api().GetErrorString(async);
+        nccl_api().CommAbort(g->comm);
+        g->comm = nullptr;
+        return MGC_E_CUDA;
+    }
+    return MGC_OK;
+}
+
+// one border exchange: pack -> grouped send/recv with both neighbours -> unpack, all enqueued on the handle's stream
+int slab_exchange(mgc_graph* g, long long* changed_dev)
+{
+    Nvtx range("mgc:slab_exchange");
+    NcclApi& N = nccl_api();
+    const unsigned P = g->L.plane;
+    const unsigned nb = (P + 255u) / 256u;
+    int32_t* h_send[2] = {(int32_t*)g->msg[0], (int32_t*)g->msg[1]};
+    double* f_send[2] = {(double*)(g->msg[0] + g->msg_h_bytes), (double*)(g->msg[1] + g->msg_h_bytes)};
+    const bool have[2] = {g->ghost_lo, g->ghost_hi};
+    for (int side = 0; side < 2; ++side) {
+        if (!have[side]) continue;
+        const size_t border = side == 0 ? (size_t)g->L.own0 * P : (size_t)(g->L.own1 - 1) * P;
+        const size_t ghost = side == 0 ? border - P : border + P;
+        k_slab_pack<double><<<nb, 256, 0, g->stream>>>(P, g->S.height + border, g->S.excess + ghost, h_send[side], f_send[side]);
+        g->st.kernel_launches++;
+    }
+    CK(cudaGetLastError());
+    if (g->comm_world > 1) {
+        NK(N.GroupStart());
+        if (have[0]) { NK(N.Send(g->msg[0], g->msg_bytes, ncclUint8, g->comm_rank - 1, g->comm, g->stream)); NK(N.Recv(g->msg[2], g->msg_bytes, ncclUint8, g->comm_rank - 1, g->comm, g->stream)); }
+        if (have[1]) { NK(N.Send(g->msg[1], g->msg_bytes, ncclUint8, g->comm_rank + 1, g->comm, g->stream)); NK(N.Recv(g->msg[3], g->msg_bytes, ncclUint8, g->comm_rank + 1, g->comm, g->stream)); }
+        NK(N.GroupEnd());
+    }
+    const int32_t* h_lo = have[0] ? (const int32_t*)g->msg[2] : nullptr;
+    const double* f_lo = have[0] ? (const double*)(g->msg[2] + g->msg_h_bytes) : nullptr;
+    const int32_t* h_hi = have[1] ? (const int32_t*)g->msg[3] : nullptr;
+    const double* f_hi = have[1] ? (const double*)(g->msg[3] + g->msg_h_bytes) : nullptr;
+    g->slab_exchanges++;
+    return mgc_slab_unpack(g, h_lo, f_lo, h_hi, f_hi, (int32_t*)changed_dev);
 }
 
 // ---- fused graph build (gc_build.cuh) ------------------------------------------------------------------
@@ -1238,6 +1402,8 @@ void mgc_destroy(mgc_graph* g)
     if (g->ev_bad) cudaEventDestroy(g->ev_bad);
     for (auto& ev : g->ev_b) if (ev) cudaEventDestroy(ev);
     if (g->h_bad) cudaFreeHost(g->h_bad);
+    if (g->h_stat) cudaFreeHost(g->h_stat);
+    slab_comm_release(g);
     if (g->up_stream) { cudaStreamSynchronize(g->up_stream); cudaStreamDestroy(g->up_stream); }
     if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
     delete g;
@@ -1524,6 +1690,7 @@ int mgc_build_voxel_graph(mgc_graph* g, const mgc_voxel_terms* t)
     if (!dtype_size(t->image->dtype)) FAIL(MGC_E_ARG, "unsupported dtype");
     CK(cudaSetDevice(g->device));
     { int rc0 = check_pending(g); if (rc0) return rc0; }
+    Nvtx range("mgc:build_voxel_graph");
     TermSpan span(g);
 
     const size_t n = (size_t)g->L.n;
@@ -1549,6 +1716,10 @@ int mgc_build_voxel_graph(mgc_graph* g, const mgc_voxel_terms* t)
         if (t->fg) { rc = stage_input(g, t->fg, 1, &d_fg); if (rc) return rc; }
         if (t->bg) { rc = stage_input(g, t->bg, 4, &d_bg); if (rc) return rc; }
         if (has_bits) {
+            if (t->bits_ready_words && t->bits_mem == MGC_MEM_HOST) {
+                while (*t->bits_ready_words < (int64_t)words) { }
+                std::atomic_thread_fence(std::memory_order_acquire);
+            }
             const uint32_t* src[2] = {t->fg_bits, t->bg_bits};
             const void** dst[2] = {&d_fg, &d_bg};
             const int slot[2] = {1, 4};
@@ -1619,6 +1790,11 @@ int mgc_build_voxel_graph(mgc_graph* g, const mgc_voxel_terms* t)
             if (t->prob) CK(cudaMemcpyAsync((char*)g->scratch[0].p + v0 * es_prob, (const char*)t->prob->data + v0 * es_prob, nv * es_prob, cudaMemcpyHostToDevice, g->up_stream));
             if (has_bits) {
                 const size_t w0 = v0 / 32, w1 = (v0 + nv + 31) / 32;
+                if (t->bits_ready_words) {        // producer thread still packing: wait until this chunk's words exist
+                    const int64_t need = (int64_t)(w1 < words ? w1 : words);
+                    while (*t->bits_ready_words < need) { /* spin: packing runs at memory speed, far ahead of PCIe */ }
+                    std::atomic_thread_fence(std::memory_order_acquire);
+                }
                 if (t->fg_bits) CK(cudaMemcpyAsync((uint32_t*)g->scratch[1].p + w0, t->fg_bits + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, g->up_stream));
                 if (t->bg_bits) CK(cudaMemcpyAsync((uint32_t*)g->scratch[4].p + w0, t->bg_bits + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, g->up_stream));
             } else {
@@ -1713,7 +1889,14 @@ int mgc_maxflow(mgc_graph* g, double* energy)
         Timer t(g, &g->st.ms_solve);
         int rc = MGC_OK;
         if (g->use_tiles) {
+            if (g->debug_checks) {
+                rc = materialise_zeros(g); if (rc) return rc;
+                if (!g->state_init) { rc = init_tiles(g); if (rc) return rc; }
+                rc = debug_invariants(g, false); if (rc) return rc;
+            }
             rc = solve_tiles(g);
+            if (rc) return rc;
+            rc = debug_invariants(g, true);
             if (rc) return rc;
         } else {
         rc = ensure_state(g);
@@ -2006,6 +2189,113 @@ int mgc_slab_finish(mgc_graph* g, double* energy_part)
     g->energy = *energy_part;
     g->st.energy = g->energy;
     g->solved = true;
+    return MGC_OK;
+}
+
+// ---- z-slab solve inside the library: NCCL point-to-point on the handle's stream, one host decision per relabel round --
+
+int mgc_slab_comm_unique_id(void* out128)
+{
+    if (!out128) return MGC_E_ARG;
+    NcclApi& N = nccl_api();
+    if (!N.ok) { g_create_error = "libnccl.so.2 could not be loaded"; return MGC_E_CUDA; }
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    if (N.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return MGC_E_CUDA; }
+    memcpy(out128, &id, sizeof(id));
+    return MGC_OK;
+}
+
+int mgc_slab_comm_init(mgc_graph* g, int32_t rank, int32_t world, const void* unique_id128)
+{
+    if (!g || !unique_id128 || world < 1 || rank < 0 || rank >= world) return MGC_E_ARG;
+    if (!g->slab) FAIL(MGC_E_STATE, "not a z-slab handle");
+    NcclApi& N = nccl_api();
+    if (!N.ok) FAIL(MGC_E_CUDA, "libnccl.so.2 could not be loaded");
+    CK(cudaSetDevice(g->device));
+    if ((rank > 0) != g->ghost_lo || (rank < world - 1) != g->ghost_hi) FAIL(MGC_E_ARG, "rank / world do not match the slab's position");
+    slab_comm_release(g);
+    ncclUniqueId id;
+    memcpy(&id, unique_id128, sizeof(id));
+    NK(N.CommInitRank(&g->comm, world, id, rank));
+    g->comm_rank = rank; g->comm_world = world;
+    const size_t P = g->L.plane;
+    g->msg_h_bytes = (P * 4 + 7) / 8 * 8;
+    g->msg_bytes = g->msg_h_bytes + P * 8;
+    void* p = nullptr;
+    for (int i = 0; i < 4; ++i) if (!g->msg[i]) { int rc = alloc_buf(g, g->msg_bytes, &p); if (rc) return rc; g->msg[i] = (char*)p; CK(cudaMemsetAsync(p, 0, g->msg_bytes, g->stream)); }
+    if (!g->d_stat) { int rc = alloc_buf(g, 64, &p); if (rc) return rc; g->d_stat = (long long*)p; }
+    if (!g->d_esum) { int rc = alloc_buf(g, 64, &p); if (rc) return rc; g->d_esum = (double*)p; }
+    if (!g->h_stat) CK(cudaHostAlloc((void**)&g->h_stat, 64, cudaHostAllocDefault));
+    return MGC_OK;
+}
+
+// The whole distributed solve (what medpy_b200/distributed.py sequenced from Python in round 1).  Distributed global
+// relabel = local BFS to a fixed point <-> border-label exchange; two rounds + the active count are enqueued
+// speculatively and checked with ONE all-reduce and ONE host synchronisation (valid iff round B changed nothing anywhere).
+// Returns the TOTAL energy (all-reduced) in *energy_total.
+int mgc_slab_solve(mgc_graph* g, double* energy_total)
+{
+    if (!g || !energy_total) return MGC_E_ARG;
+    if (!g->slab || !g->comm) FAIL(MGC_E_STATE, "call mgc_slab_comm_init first");
+    NcclApi& N = nccl_api();
+    CK(cudaSetDevice(g->device));
+    int rc = mgc_slab_begin(g);
+    if (rc) return rc;
+    g->slab_exchanges = g->slab_relabel_rounds = g->slab_push_passes = g->slab_global_relabels = 0;
+    int passes = g->passes0 > 0 ? g->passes0 : 1;
+    const int passes_cap = g->passes_max < 8 ? g->passes_max : 8;
+    int64_t rounds = 0;
+    for (;;) {
+        rc = mgc_slab_relabel_begin(g);
+        if (rc) return rc;
+        for (;;) {
+            CK(cudaMemsetAsync(g->d_stat, 0, 3 * sizeof(long long), g->stream));
+            for (int k = 0; k < 2; ++k) {
+                rc = mgc_slab_relabel_relax(g, nullptr);
+                if (rc) return rc;
+                rc = slab_exchange(g, g->d_stat + k);
+                if (rc) return rc;
+                g->slab_relabel_rounds++;
+            }
+            rc = mgc_slab_count_active_dev(g, (unsigned long long*)(g->d_stat + 2));
+            if (rc) return rc;
+            if (g->comm_world > 1) NK(N.AllReduce(g->d_stat, g->d_stat, 3, ncclInt64, ncclSum, g->comm, g->stream));
+            CK(cudaMemcpyAsync(g->h_stat, g->d_stat, 3 * sizeof(long long), cudaMemcpyDeviceToHost, g->stream));
+            CK(cudaStreamSynchronize(g->stream));                     // the one host decision of this round
+            rc = slab_comm_poll(g);
+            if (rc) return rc;
+            if (g->h_stat[1] == 0) break;
+        }
+        g->slab_global_relabels++;
+        if (g->h_stat[2] == 0) break;
+        if (++rounds > g->max_rounds) FAIL(MGC_E_NOCONV, "push-relabel did not converge within the round cap");
+        for (int p = 0; p < passes; ++p) {
+            rc = mgc_slab_push(g, 1);
+            if (rc) return rc;
+            rc = slab_exchange(g, nullptr);
+            if (rc) return rc;
+            g->slab_push_passes++;
+        }
+        passes = passes * 2 > passes_cap ? passes_cap : passes * 2;
+    }
+    double part = 0.0;
+    rc = mgc_slab_finish(g, &part);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(g->d_esum, &part, sizeof(double), cudaMemcpyHostToDevice, g->stream));
+    if (g->comm_world > 1) NK(N.AllReduce(g->d_esum, g->d_esum, 1, ncclFloat64, ncclSum, g->comm, g->stream));
+    CK(cudaMemcpyAsync(energy_total, g->d_esum, sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    return slab_comm_poll(g);
+}
+
+int mgc_slab_solve_stats(const mgc_graph* g, int64_t* exchanges, int64_t* relabel_rounds, int64_t* push_passes, int64_t* global_relabels)
+{
+    if (!g) return MGC_E_ARG;
+    if (exchanges) *exchanges = g->slab_exchanges;
+    if (relabel_rounds) *relabel_rounds = g->slab_relabel_rounds;
+    if (push_passes) *push_passes = g->slab_push_passes;
+    if (global_relabels) *global_relabels = g->slab_global_relabels;
     return MGC_OK;
 }
 

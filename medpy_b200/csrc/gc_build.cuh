@@ -85,13 +85,18 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
     const bool spacing = SPACING >= 0 ? (SPACING != 0) : (P.inv_spacing_on != 0.0);
 
     // ---- stage the image block with halo: local (hz, hy, hx) <-> global (z0 - 1 + hz, y0 - 1 + hy, x0 - 1 + hx) ----
+    // TMA: box start coordinates must not be negative (measured on B200: a negative start coordinate raises "illegal
+    // instruction" in UTMALDG, compute-sanitizer log in profiles/), so a block on a low face of the lattice starts its box
+    // at 0 and the shared-memory index is shifted by one instead -- the halo cells in front of the lattice are never read.
+    // Parts of the box beyond the high faces are zero-filled by the TMA unit.
+    const int ox = (A.use_tma && x0 == 0) ? 1 : 0, oy = (A.use_tma && y0 == 0) ? 1 : 0, oz = (A.use_tma && z0 == 0) ? 1 : 0;
     if (tid < 8) s_flags[tid] = 0;
     if (A.use_tma) {
         if (tid == 0) {
             mbar_init(bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             mbar_expect_tx(bar, (unsigned)IMG_BYTES);
-            tma_load_3d(s_img, &imap, bar, x0 - 1, y0 - 1, z0 - 1);
+            tma_load_3d(s_img, &imap, bar, x0 - 1 + ox, y0 - 1 + oy, z0 - 1 + oz);
         }
         __syncthreads();
         mbar_wait(bar, 0u);
@@ -112,7 +117,7 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
     const bool col_in = gy < L.dim[1] && gx < L.dim[2];
     const bool has_py = gy + 1 < L.dim[1], has_px = gx + 1 < L.dim[2];
     const double sp_z = spacing ? P.spacing[0] : 1.0, sp_y = spacing ? P.spacing[1] : 1.0, sp_x = spacing ? P.spacing[2] : 1.0;
-    auto at = [&](int hz, int hy, int hx) -> E { return s_img[(hz * BUILD_HY + hy) * BUILD_BX + hx]; };
+    auto at = [&](int hz, int hy, int hx) -> E { return s_img[((hz - oz) * BUILD_HY + (hy - oy)) * BUILD_BX + (hx - ox)]; };
 
     int isbad = 0;
     unsigned needs_any = 0, exc_any = 0;

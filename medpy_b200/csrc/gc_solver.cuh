@@ -241,3 +241,46 @@ __global__ void k_slab_unpack(unsigned plane, int* __restrict__ height_ghost, T*
         cap_border_to_ghost[i] += (T)f;
     }
 }
+
+// ---------------------------------------------------------------------------------------------------
+// debug-mode invariants (MEDPY_GC_DEBUG=1): out[0] += excess, out[1] += flow absorbed by the sink links,
+// out[2] += violations of: excess >= 0, every residual capacity >= 0, absorbed flow within [0, sink capacity], and (tile
+// solver, CHECK_RMASK) every residual-mask bit equal to "capacity > 0".  Flow conservation is checked by the host:
+// sum(excess) + sum(absorbed) must equal the clamped source excess the solve started from.
+// ---------------------------------------------------------------------------------------------------
+template <int ND, typename T, bool CHECK_RMASK>
+__global__ void __launch_bounds__(256) k_debug_invariants(Lattice L, State<T> S, double* __restrict__ out)
+{
+    const unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0, a = 0.0;
+    unsigned long long bad = 0;
+    if (v < L.n && owned(L, v)) {
+        e = (double)S.excess[v];
+        if (!(e >= 0.0)) bad++;
+        const double tr = (double)S.tr[v];
+        const unsigned m = S.rmask[v];
+        const bool lazy = CHECK_RMASK;      // 3-D tile solver: sink[] valid only where bit 7 of rmask is set
+        if (tr < 0) {
+            a = (!lazy || (m & 0x80u)) ? (double)S.sink[v] : 0.0;
+            if (!(a >= 0.0) || a > -tr) bad++;
+            if (CHECK_RMASK && (((m & 0x40u) != 0) != ((-tr) - a > 0))) bad++;
+        }
+#pragma unroll
+        for (int k = 0; k < 2 * ND; ++k) {
+            const double c = (double)S.cap[k][v];
+            if (c < 0.0) bad++;
+            if (CHECK_RMASK && (((m >> k) & 1u) != (c > 0 ? 1u : 0u))) bad++;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        e += __shfl_down_sync(0xffffffffu, e, o);
+        a += __shfl_down_sync(0xffffffffu, a, o);
+        bad += __shfl_down_sync(0xffffffffu, bad, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (e != 0.0) atomicAdd(out, e);
+        if (a != 0.0) atomicAdd(out + 1, a);
+        if (bad) atomicAdd(out + 2, (double)bad);
+    }
+}

@@ -61,6 +61,13 @@ class SlabSolver:
             self.tdev = torch.device("cuda", self.device_index)
             self.handle = _native_factory(self.shape, self.z0, self.z1, self.device_index)
             self.handle.set_stream(torch.cuda.current_stream(self.tdev).cuda_stream)
+            # the solve runs inside the library over its own NCCL communicator (mgc_slab_solve); torch.distributed only
+            # carries the 128-byte unique id.  MEDPY_GC_SLAB_HOST_LOOP=1 keeps the round-1 Python-sequenced loop (A/B).
+            self.native_loop = self.world > 1 and os.environ.get("MEDPY_GC_SLAB_HOST_LOOP", "0") != "1"
+            if self.native_loop:
+                box = [type(self.handle).slab_comm_unique_id() if self.rank == 0 else None]
+                dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+                self.handle.slab_comm_init(self.rank, self.world, box[0])
         else:
             self.tdev = torch.device("cpu")
             self.handle = handle_factory(self.shape, self.z0, self.z1)
@@ -179,6 +186,12 @@ class SlabSolver:
     def solve(self, max_rounds=100000):
         """Run to a maximum preflow.  Returns this rank's energy share; use ``energy()`` for the total."""
         self.stats = {"exchanges": 0, "relabel_rounds": 0, "global_relabels": 0, "push_passes": 0}   # per solve
+        self.energy_total = None
+        if self.native and getattr(self, "native_loop", False):
+            self.energy_total = float(self.handle.slab_solve())
+            self.stats = dict(self.handle.slab_solve_stats())
+            self.energy_part = None
+            return self.energy_total
         self.handle.slab_begin()
         passes = self.passes0
         rounds = 0
@@ -198,6 +211,8 @@ class SlabSolver:
 
     def energy(self):
         """Total min-cut energy (float64 all-reduce of the per-slab parts)."""
+        if getattr(self, "energy_total", None) is not None:
+            return self.energy_total
         t = self.torch.tensor([self.energy_part], dtype=self.torch.float64, device=self.tdev)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return float(t.item())
