@@ -78,7 +78,7 @@ def build_lib(force=False, verbose=False):
 
 def build_ext(force=False):
     src = os.path.join(CSRC, "gc_pybind.cpp")
-    if not force and not _newer(EXT, [src, LIB, os.path.join(INCLUDE, "medpy_b200_graphcut.h")]):
+    if not force and not _newer(EXT, [src, LIB, os.path.join(INCLUDE, "medpy_b200_graphcut.h"), os.path.join(CSRC, "host_pack.hpp")]):
         return EXT
     import pybind11
     cmd = [CXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden",

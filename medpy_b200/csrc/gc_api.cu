@@ -1282,7 +1282,15 @@ bool make_image_map(mgc_graph* g, const void* img, int dtype, CUtensorMap* out)
     }
     const cuuint64_t dims[3] = {X, Y, Z};
     const cuuint64_t strides[2] = {X * es, X * Y * es};
-    const cuuint32_t box[3] = {BUILD_BX, BUILD_HY, BUILD_HZ};
+    cuuint32_t bx = 0;
+    switch (dtype) {
+        case MGC_F32: bx = BuildBox<float>::BX; break;
+        case MGC_F64: bx = BuildBox<double>::BX; break;
+        case MGC_U8: bx = BuildBox<uint8_t>::BX; break;
+        case MGC_I16: bx = BuildBox<int16_t>::BX; break;
+        default: bx = BuildBox<int32_t>::BX; break;
+    }
+    const cuuint32_t box[3] = {bx, BUILD_HY, BUILD_HZ};
     const cuuint32_t estr[3] = {1, 1, 1};
     return encode(out, dt, 3, const_cast<void*>(img), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -1999,7 +2007,7 @@ int mgc_get_trcap(mgc_graph* g, int64_t node, double* trcap)
     if (!g || !trcap) return MGC_E_ARG;
     if (node < 0 || node >= (int64_t)g->L.n) FAIL(MGC_E_ARG, "node id out of range");
     if (g->tr_fresh) { *trcap = 0.0; return MGC_OK; }
-    if (!g->state_init) {
+    if (!g->state_init || !g->flow_started) {      // no flow yet: the net terminal capacity exactly as add_tweights left it
         CK(cudaMemcpyAsync(trcap, g->S.tr + node, sizeof(double), cudaMemcpyDeviceToHost, g->stream));
         CK(cudaStreamSynchronize(g->stream));
         return MGC_OK;

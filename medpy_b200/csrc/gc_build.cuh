@@ -13,7 +13,7 @@
 // entry has been written, see gc_tiles.cuh.)
 //
 // Geometry: a 256-thread CTA builds an 8 (z) x 8 (y) x 32 (x) block = four 8^3 solver tiles in a row.  The image
-// block with a one-voxel halo on every side (10 x 10 x 34, box 10 x 10 x BUILD_BX) is staged in shared memory by ONE
+// block with a one-voxel halo on every side (10 x 10 x 34, box 10 x 10 x BuildBox<E>::BX) is staged in shared memory by ONE
 // `cp.async.bulk.tensor.3d` box copy against a per-call tensor map (SASS: UTMALDG + SYNCS; out-of-lattice parts are
 // zero-filled by the TMA unit and masked by coordinates), or by plain loads when the image does not meet the 16-byte
 // stride rule of tensor maps.  Thread (y, x) marches through z = -1 .. 7: per step it evaluates the three FORWARD
@@ -30,7 +30,14 @@
 #define BUILD_TY 8
 #define BUILD_TX 32
 #define BUILD_THREADS 256
-#define BUILD_BX 48            // inner box extent: >= 34 and a multiple of 16 bytes for every element size
+// Inner (x) extent of the staged image block.  Measured on B200: UTMALDG raises "illegal instruction" when the box
+// start along the innermost axis is negative or not 16-byte aligned, so the box starts BUILD_PAD = 16 / sizeof(E)
+// elements in front of the block (x0 is a multiple of 32) instead of 1, or at 0 for the blocks on the low x face; the
+// extent covers pad + 32 + 1 elements, rounded up to a multiple of 16 bytes.
+template <typename E> struct BuildBox {
+    static constexpr int PAD = 16 / (int)sizeof(E);
+    static constexpr int BX = (PAD + 33 + PAD - 1) / PAD * PAD;      // f32 40, f64 36, u8 64, i16 48, i32 40
+};
 #define BUILD_HY 10
 #define BUILD_HZ 10
 
@@ -69,6 +76,7 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
              int* __restrict__ pflag, WorkList pl0, WorkList pl1)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int BUILD_BX = BuildBox<E>::BX, BUILD_PAD = BuildBox<E>::PAD;
     E* s_img = reinterpret_cast<E*>(smem_raw);                                   // [10][10][BUILD_BX]
     constexpr int IMG_BYTES = BUILD_HZ * BUILD_HY * BUILD_BX * (int)sizeof(E);
     constexpr int IMG_PAD = (IMG_BYTES + 127) / 128 * 128;
@@ -85,18 +93,19 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
     const bool spacing = SPACING >= 0 ? (SPACING != 0) : (P.inv_spacing_on != 0.0);
 
     // ---- stage the image block with halo: local (hz, hy, hx) <-> global (z0 - 1 + hz, y0 - 1 + hy, x0 - 1 + hx) ----
-    // TMA: box start coordinates must not be negative (measured on B200: a negative start coordinate raises "illegal
-    // instruction" in UTMALDG, compute-sanitizer log in profiles/), so a block on a low face of the lattice starts its box
-    // at 0 and the shared-memory index is shifted by one instead -- the halo cells in front of the lattice are never read.
-    // Parts of the box beyond the high faces are zero-filled by the TMA unit.
-    const int ox = (A.use_tma && x0 == 0) ? 1 : 0, oy = (A.use_tma && y0 == 0) ? 1 : 0, oz = (A.use_tma && z0 == 0) ? 1 : 0;
+    // TMA: the box starts at a non-negative, 16-byte aligned x (see BuildBox) and at non-negative y / z: blocks on a low
+    // face start at 0 and the shared-memory index is shifted instead -- the halo cells in front of the lattice are never
+    // read.  Parts of the box beyond the high faces are zero-filled by the TMA unit.  cx / cy / cz: shared-memory index of
+    // the logical halo cell 0 (global x0 - 1, y0 - 1, z0 - 1) along each axis.
+    const int cx = A.use_tma ? (x0 == 0 ? -1 : BUILD_PAD - 1) : 0;
+    const int cy = (A.use_tma && y0 == 0) ? -1 : 0, cz = (A.use_tma && z0 == 0) ? -1 : 0;
     if (tid < 8) s_flags[tid] = 0;
     if (A.use_tma) {
         if (tid == 0) {
             mbar_init(bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             mbar_expect_tx(bar, (unsigned)IMG_BYTES);
-            tma_load_3d(s_img, &imap, bar, x0 - 1 + ox, y0 - 1 + oy, z0 - 1 + oz);
+            tma_load_3d(s_img, &imap, bar, x0 - 1 - cx, y0 - 1 - cy, z0 - 1 - cz);
         }
         __syncthreads();
         mbar_wait(bar, 0u);
@@ -117,7 +126,7 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
     const bool col_in = gy < L.dim[1] && gx < L.dim[2];
     const bool has_py = gy + 1 < L.dim[1], has_px = gx + 1 < L.dim[2];
     const double sp_z = spacing ? P.spacing[0] : 1.0, sp_y = spacing ? P.spacing[1] : 1.0, sp_x = spacing ? P.spacing[2] : 1.0;
-    auto at = [&](int hz, int hy, int hx) -> E { return s_img[((hz - oz) * BUILD_HY + (hy - oy)) * BUILD_BX + (hx - ox)]; };
+    auto at = [&](int hz, int hy, int hx) -> E { return s_img[((hz + cz) * BUILD_HY + (hy + cy)) * BUILD_BX + (hx + cx)]; };
 
     int isbad = 0;
     unsigned needs_any = 0, exc_any = 0;
@@ -267,7 +276,7 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
 template <typename E>
 constexpr size_t build_smem_bytes()
 {
-    return (size_t)((BUILD_HZ * BUILD_HY * BUILD_BX * sizeof(E) + 127) / 128 * 128) + (2 * 9 * 32 + 2 * 8 * 33) * sizeof(double) + 8 + 8 * sizeof(int) +
+    return (size_t)((BUILD_HZ * BUILD_HY * BuildBox<E>::BX * sizeof(E) + 127) / 128 * 128) + (2 * 9 * 32 + 2 * 8 * 33) * sizeof(double) + 8 + 8 * sizeof(int) +
            8 * sizeof(double) + 64;
 }
 

@@ -66,6 +66,10 @@ def _snapshot(g, shape, count=4000, seed=0):
     ((12, 20, 40), "difference_division", True, (1.5, 0.5, 2.0), numpy.float64),
     ((16, 16, 48), "difference_linear", False, False, numpy.float32),
     ((10, 12, 16), "maximum_power", True, False, numpy.int16),
+    ((6, 10, 80), "maximum_power", False, False, numpy.int16),                 # several x blocks, 2-byte elements (TMA box pad 8)
+    ((8, 9, 96), "difference_division", False, False, numpy.uint8),            # 1-byte elements (TMA box pad 16)
+    ((5, 18, 72), "difference_exponential", True, False, numpy.float64),
+    ((8, 8, 104), "difference_linear", False, False, numpy.int32),
     ((7, 40), "difference_exponential", True, False, numpy.float32),           # 2-D input on the 3-D kernels
     ((50,), "difference_exponential", False, False, numpy.float32),
 ])
@@ -73,7 +77,9 @@ def test_fused_build_equals_per_term_kernels(shape, kind, regional, spacing, dty
     from medpy_b200 import synthetic
     vol = synthetic.two_blob_volume(shape, seed=3)
     img = vol["image"]
-    if numpy.issubdtype(dtype, numpy.integer):
+    if dtype == numpy.uint8:
+        img = numpy.clip(numpy.round(img + 60.0), 0, 255).astype(dtype)
+    elif numpy.issubdtype(dtype, numpy.integer):
         img = numpy.round(img).astype(dtype)
     else:
         img = img.astype(dtype)
