@@ -611,6 +611,10 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
         if (const char* e1 = getenv("MEDPY_GC_ITERS")) if (atoi(e1) > 0) g->tile_iters = atoi(e1);
         if (const char* e2 = getenv("MEDPY_GC_PASSES0")) if (atoi(e2) > 0) g->passes0 = atoi(e2);
         if (const char* e3 = getenv("MEDPY_GC_PASSES_MAX")) if (atoi(e3) > 0) g->passes_max = atoi(e3);
+        if (const char* e7 = getenv("MEDPY_GC_SWEEP")) g->use_sweeps = atoi(e7) != 0;
+        if (const char* e8 = getenv("MEDPY_GC_SWEEP_FRAC")) if (atoi(e8) > 0) g->sweep_frac = atoi(e8);
+        if (const char* e9 = getenv("MEDPY_GC_SWEEP_ROUNDS")) if (atoi(e9) > 0) g->sweep_rounds_max = atoi(e9);
+        if (const char* e10 = getenv("MEDPY_GC_SWEEP_DONE_FRAC")) if (atoi(e10) > 0) g->sweep_done_frac = atoi(e10);
     }
     if (rc) { g_create_error = g->err; mgc_destroy(g); return rc; }
     if (cudaStreamCreate(&g->stream) != cudaSuccess) { g_create_error = "cudaStreamCreate failed"; mgc_destroy(g); return MGC_E_CUDA; }
@@ -874,14 +878,19 @@ int relabel_tiles_begin(mgc_graph* g)
 // point yet (gc_sweep.cuh); *pending = number of such tiles (host synchronisation)
 int relabel_sweep_round(mgc_graph* g, int* pending)
 {
-    for (int a = 0; a < 2; ++a) {
+    const int last = g->nd - 1;
+    for (int a = 0; a < last; ++a) {
         if (g->L.dim[a] < 2) continue;
         const unsigned nlines = g->L.n / (unsigned)g->L.dim[a];
         k_sweep_axis<<<(nlines + 255u) / 256u, 256, 0, g->stream>>>(g->L, g->S.rmask, g->S.height, a);
         g->st.kernel_launches++;
     }
-    if (g->L.dim[2] >= 2) {
-        const unsigned nrows = g->L.n / (unsigned)g->L.dim[2];
+    if (g->L.dim[last] >= 2 && g->L.dim[last] <= SWEEP_SHORT) {
+        const unsigned nrows = g->L.n / (unsigned)g->L.dim[last];
+        k_sweep_rows_short<<<(nrows + 255u) / 256u, 256, 0, g->stream>>>(g->L, g->S.rmask, g->S.height);
+        g->st.kernel_launches++;
+    } else if (g->L.dim[last] >= 2) {
+        const unsigned nrows = g->L.n / (unsigned)g->L.dim[last];
         unsigned grid = (nrows + SWEEP_WARPS - 1) / SWEEP_WARPS;
         const unsigned cap = (unsigned)cached_sm_count(g->device) * 16u;
         if (grid > cap) grid = cap;
@@ -890,7 +899,8 @@ int relabel_sweep_round(mgc_graph* g, int* pending)
     }
     CK(cudaMemsetAsync(g->d_tcount, 0, 2 * sizeof(int), g->stream));
     CK(cudaMemsetAsync(g->rflag, 0, (size_t)g->TL.ntiles * sizeof(int), g->stream));
-    k_relabel_check<<<nblocks(g), 256, 0, g->stream>>>(g->L, g->TL, g->S.rmask, g->S.height, g->rflag, rl(g, 0));
+    if (g->nd == 4) k_relabel_check4<<<nblocks(g), 256, 0, g->stream>>>(g->L, g->TL4, g->S.rmask, g->S.height, g->rflag, rl(g, 0));
+    else            k_relabel_check<<<nblocks(g), 256, 0, g->stream>>>(g->L, g->TL, g->S.rmask, g->S.height, g->rflag, rl(g, 0));
     g->st.kernel_launches++;
     g->rl_cur = 0;
     CK(cudaMemsetAsync(g->d_tcount + CTL_RLCUR, 0, sizeof(int), g->stream));
@@ -902,7 +912,7 @@ int relabel_sweep_round(mgc_graph* g, int* pending)
 int relabel_tiles_run(mgc_graph* g, int* any, bool want_any = true)
 {
     *any = 0;
-    if (g->use_sweeps && g->nd == 3 && g->TL.ntiles >= 64) {
+    if (g->use_sweeps && g->use_tiles && g->TL.ntiles >= 64) {
         int pending = 0;
         int rc = read_tcount(g, g->rl_cur, &pending);
         if (rc) return rc;
@@ -1631,8 +1641,8 @@ int mgc_add_markers(mgc_graph* g, const mgc_array* fg, const mgc_array* bg)
 int mgc_add_boundary(mgc_graph* g, int32_t kind, const mgc_array* image, double sigma, const double* spacing, double norm)
 {
     if (!g || !image) return MGC_E_ARG;
-    if (g->flow_started) FAIL(MGC_E_STATE, "the graph has been solved (its capacities hold residuals): reset() it before adding terms");
     if (kind < 0 || kind > 7) FAIL(MGC_E_ARG, "unknown boundary term");
+    if (g->flow_started) FAIL(MGC_E_STATE, "the graph has been solved (its capacities hold residuals): reset() it before adding terms");
     CK(cudaSetDevice(g->device));
     { int rc0 = check_pending(g); if (rc0) return rc0; }
     TermSpan t(g);

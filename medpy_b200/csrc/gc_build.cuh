@@ -82,7 +82,7 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
     constexpr int IMG_PAD = (IMG_BYTES + 127) / 128 * 128;
     double* s_wy = reinterpret_cast<double*>(smem_raw + IMG_PAD);                // [2][9][32]: +y weight of row y-1 .. 7
     double* s_wx = s_wy + 2 * 9 * 32;                                            // [2][8][33]: +x weight of column x-1 .. 31
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(s_wx + 2 * 8 * 33);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(s_wx + 2 * 8 * 33 + 8 * 32 + 8 * 8);
     int* s_flags = reinterpret_cast<int*>(bar + 1);                              // [4] needs, [4] has excess
     double* s_red = reinterpret_cast<double*>(s_flags + 8);                      // [8] block reduction
 
@@ -126,19 +126,39 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
     const bool col_in = gy < L.dim[1] && gx < L.dim[2];
     const bool has_py = gy + 1 < L.dim[1], has_px = gx + 1 < L.dim[2];
     const double sp_z = spacing ? P.spacing[0] : 1.0, sp_y = spacing ? P.spacing[1] : 1.0, sp_x = spacing ? P.spacing[2] : 1.0;
-    auto at = [&](int hz, int hy, int hx) -> E { return s_img[((hz + cz) * BUILD_HY + (hy + cy)) * BUILD_BX + (hx + cx)]; };
+    // (cells in front of the lattice do not exist when the box was clamped: their index is clamped too, the value is
+    // never used -- every pair that would need it is invalid)
+    auto at = [&](int hz, int hy, int hx) -> E {
+        const int i = ((hz + cz) * BUILD_HY + (hy + cy)) * BUILD_BX + (hx + cx);
+        return s_img[i < 0 ? 0 : i];
+    };
 
     int isbad = 0;
     unsigned needs_any = 0, exc_any = 0;
     double msum = 0.0;
-    // -z capacity of the first plane: pair (z0 - 1, z0)
-    double wz_back = 0.0;
-    if (col_in && z0 > 0 && z0 < L.dim[0]) {
-        const double a = build_val<E>(at(0, ly + 1, lx + 1), use_max);
-        double w = build_pair<FN, E>(P, a, at(1, ly + 1, lx + 1), use_max);
-        if (spacing) w = __ddiv_rn(w, sp_z);
-        if (w <= 0.0) isbad = 1;
-        wz_back = w;
+    // one pair weight: value of the neighbour cell, validity, axis spacing
+    auto pair_w = [&](double a, E iq, bool valid, double sp) -> double {
+        double w = build_pair<FN, E>(P, a, iq, use_max);
+        if (spacing) w = __ddiv_rn(w, sp);
+        if (valid && w <= 0.0) isbad = 1;
+        return valid ? w : 0.0;
+    };
+    // ---- prologue: the weights on the block's three LOW faces, spread over all threads (one z-face and one y-face
+    // weight per thread, the 64 x-face weights on the first two warps) so that no warp carries extra work in the loop ----
+    double* s_wyh = s_wx + 2 * 8 * 33;          // [8 z][32 x]: pair (y0 - 1, y0)
+    double* s_wxh = s_wyh + 8 * 32;             // [8 z][8 y]:  pair (x0 - 1, x0)
+    double wz_back;
+    {
+        const bool vz = col_in && z0 > 0;
+        wz_back = pair_w(build_val<E>(at(0, ly + 1, lx + 1), use_max), at(1, ly + 1, lx + 1), vz, sp_z);
+        // thread (ly, lx) -> y-face weight of plane z0 + ly at column x0 + lx
+        const bool vy = y0 > 0 && gx < L.dim[2] && z0 + ly < L.dim[0];
+        s_wyh[ly * 32 + lx] = pair_w(build_val<E>(at(ly + 1, 0, lx + 1), use_max), at(ly + 1, 1, lx + 1), vy, sp_y);
+        if (tid < 64) {
+            const int fz = tid >> 3, fy = tid & 7;
+            const bool vx = x0 > 0 && y0 + fy < L.dim[1] && z0 + fz < L.dim[0];
+            s_wxh[fz * 8 + fy] = pair_w(build_val<E>(at(fz + 1, fy + 1, 0), use_max), at(fz + 1, fy + 1, 1), vx, sp_x);
+        }
     }
 
     for (int lz = 0; lz < BUILD_TZ; ++lz) {
@@ -147,41 +167,19 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
         double* wyb = s_wy + (lz & 1) * 9 * 32;
         double* wxb = s_wx + (lz & 1) * 8 * 33;
         const int hz = lz + 1;
-        double wz = 0.0, wy = 0.0, wx = 0.0;
-        if (gz < L.dim[0]) {
-            if (pin) {
-                const double a = build_val<E>(at(hz, ly + 1, lx + 1), use_max);
-                if (gz + 1 < L.dim[0]) { wz = build_pair<FN, E>(P, a, at(hz + 1, ly + 1, lx + 1), use_max); if (spacing) wz = __ddiv_rn(wz, sp_z); if (wz <= 0.0) isbad = 1; }
-                if (has_py) { wy = build_pair<FN, E>(P, a, at(hz, ly + 2, lx + 1), use_max); if (spacing) wy = __ddiv_rn(wy, sp_y); if (wy <= 0.0) isbad = 1; }
-                if (has_px) { wx = build_pair<FN, E>(P, a, at(hz, ly + 1, lx + 2), use_max); if (spacing) wx = __ddiv_rn(wx, sp_x); if (wx <= 0.0) isbad = 1; }
-            }
-            wyb[(ly + 1) * 32 + lx] = wy;
-            wxb[ly * 33 + lx + 1] = wx;
-            // low faces of the block: pair (y0 - 1, y0) by warp 0, pair (x0 - 1, x0) by the first 8 lanes of warp 1
-            if (ly == 0) {
-                double w = 0.0;
-                if (y0 > 0 && gx < L.dim[2]) {
-                    const double a = build_val<E>(at(hz, 0, lx + 1), use_max);
-                    w = build_pair<FN, E>(P, a, at(hz, 1, lx + 1), use_max);
-                    if (spacing) w = __ddiv_rn(w, sp_y);
-                    if (w <= 0.0) isbad = 1;
-                }
-                wyb[lx] = w;
-            } else if (ly == 1 && lx < 8) {
-                double w = 0.0;
-                if (x0 > 0 && y0 + lx < L.dim[1]) {
-                    const double a = build_val<E>(at(hz, lx + 1, 0), use_max);
-                    w = build_pair<FN, E>(P, a, at(hz, lx + 1, 1), use_max);
-                    if (spacing) w = __ddiv_rn(w, sp_x);
-                    if (w <= 0.0) isbad = 1;
-                }
-                wxb[lx * 33] = w;
-            }
-        }
+        // the three forward pair weights of this voxel: independent, branch-free evaluations
+        const double a = build_val<E>(at(hz, ly + 1, lx + 1), use_max);
+        const double wz = pair_w(a, at(hz + 1, ly + 1, lx + 1), pin && gz + 1 < L.dim[0], sp_z);
+        const double wy = pair_w(a, at(hz, ly + 2, lx + 1), pin && has_py, sp_y);
+        const double wx = pair_w(a, at(hz, ly + 1, lx + 2), pin && has_px, sp_x);
+        wyb[(ly + 1) * 32 + lx] = wy;
+        wxb[ly * 33 + lx + 1] = wx;
         __syncthreads();
         if (pin) {
             const unsigned v = (unsigned)gz * L.stride[0] + (unsigned)gy * L.stride[1] + (unsigned)gx;
-            const double c0 = wz_back, c1 = wz, c2 = wyb[ly * 32 + lx], c3 = wy, c4 = wxb[ly * 33 + lx], c5 = wx;
+            const double c0 = wz_back, c1 = wz, c3 = wy, c5 = wx;
+            const double c2 = ly ? wyb[ly * 32 + lx] : s_wyh[lz * 32 + lx];
+            const double c4 = lx ? wxb[ly * 33 + lx] : s_wxh[lz * 8 + ly];
             S.cap[0][v] = (T)c0; S.cap[1][v] = (T)c1; S.cap[2][v] = (T)c2;
             S.cap[3][v] = (T)c3; S.cap[4][v] = (T)c4; S.cap[5][v] = (T)c5;
             // ---- t-links: add_tweights replay in the reference's order (regional, fg, bg) ----
@@ -276,7 +274,7 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
 template <typename E>
 constexpr size_t build_smem_bytes()
 {
-    return (size_t)((BUILD_HZ * BUILD_HY * BuildBox<E>::BX * sizeof(E) + 127) / 128 * 128) + (2 * 9 * 32 + 2 * 8 * 33) * sizeof(double) + 8 + 8 * sizeof(int) +
+    return (size_t)((BUILD_HZ * BUILD_HY * BuildBox<E>::BX * sizeof(E) + 127) / 128 * 128) + (2 * 9 * 32 + 2 * 8 * 33 + 8 * 32 + 8 * 8) * sizeof(double) + 8 + 8 * sizeof(int) +
            8 * sizeof(double) + 64;
 }
 

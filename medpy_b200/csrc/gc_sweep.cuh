@@ -18,6 +18,7 @@
 // voxels are relabelled (ghost planes of a z-slab are inputs).
 #pragma once
 #include "gc_tiles.cuh"
+#include "gc_tiles4.cuh"
 
 #define SWEEP_UNROLL 8
 
@@ -224,6 +225,35 @@ __global__ void __launch_bounds__(32 * SWEEP_WARPS) k_sweep_rows(Lattice L, cons
     }
 }
 
+// short rows (fastest axis of <= SWEEP_SHORT voxels, e.g. the 4 channels of a multi-spectral 4-D image): one THREAD per
+// row, forward then backward; consecutive threads read consecutive rows, so the loads still coalesce.
+#define SWEEP_SHORT 32
+__global__ void __launch_bounds__(256) k_sweep_rows_short(Lattice L, const uint8_t* __restrict__ rmask, int* __restrict__ height)
+{
+    const int ax = L.nd - 1;
+    const int X = L.dim[ax];
+    const unsigned nrows = L.n / (unsigned)X;
+    const unsigned row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    const unsigned g = row * (unsigned)X;
+    const int z = (int)(g / L.stride[0]);
+    if (z < L.own0 || z >= L.own1) return;
+    const unsigned bit_m = 1u << (2 * ax), bit_p = 1u << (2 * ax + 1);
+    int h[SWEEP_SHORT];
+    unsigned m[SWEEP_SHORT];
+#pragma unroll
+    for (int x = 0; x < SWEEP_SHORT; ++x) if (x < X) { h[x] = __ldcg(height + g + x); m[x] = rmask[g + x]; }
+    unsigned changed = 0;
+#pragma unroll
+    for (int x = 1; x < SWEEP_SHORT; ++x)
+        if (x < X && (m[x] & bit_m)) { const int c = sweep_inc(h[x - 1]); if (c < h[x]) { h[x] = c; changed |= 1u << x; } }
+#pragma unroll
+    for (int x = SWEEP_SHORT - 2; x >= 0; --x)
+        if (x + 1 < X && (m[x] & bit_p)) { const int c = sweep_inc(h[x + 1]); if (c < h[x]) { h[x] = c; changed |= 1u << x; } }
+#pragma unroll
+    for (int x = 0; x < SWEEP_SHORT; ++x) if (x < X && (changed >> x) & 1u) height[g + x] = h[x];
+}
+
 // ---------------------------------------------------------------------------------------------------
 // fixed-point check: lists (relabel worklist `rl`, flags `rflag`, both zeroed by the host) every 8^3 tile that holds
 // an owned voxel whose label can still drop given its residual neighbours' labels.  One thread per voxel, neighbour
@@ -250,6 +280,33 @@ __global__ void __launch_bounds__(256) k_relabel_check(Lattice L, Tiles TL, cons
         }
     if (best < h) {
         const int t = ((c[0] >> 3) * TL.nt[1] + (c[1] >> 3)) * TL.nt[2] + (c[2] >> 3);
+        if (*(volatile int*)(rflag + t) == 0) list_push(rflag, rl, t);
+    }
+}
+
+// 4-D lattices (4 x 4 x 8 x 4 tiles of gc_tiles4.cuh; all eight mask bits are arcs, the sink flag lives in smask and is
+// not needed here: labels 1 are already in place)
+__global__ void __launch_bounds__(256) k_relabel_check4(Lattice L, Tiles4 TL, const uint8_t* __restrict__ rmask,
+                                                        const int* __restrict__ height, int* __restrict__ rflag, WorkList rl)
+{
+    const unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= L.n) return;
+    const unsigned m = rmask[v];
+    if (!m) return;
+    const int h = __ldcg(height + v);
+    if (h <= 1) return;
+    int c[4];
+    decode<4>(L, v, c);
+    if (c[0] < L.own0 || c[0] >= L.own1) return;
+    int best = h;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (m & (1u << k)) {
+            const int hw = sweep_inc(__ldcg(height + (unsigned)((int)v + dir_offset(L, k))));
+            best = hw < best ? hw : best;
+        }
+    if (best < h) {
+        const int t = (((c[0] >> 2) * TL.nt[1] + (c[1] >> 2)) * TL.nt[2] + (c[2] >> 3)) * TL.nt[3] + (c[3] >> 2);
         if (*(volatile int*)(rflag + t) == 0) list_push(rflag, rl, t);
     }
 }

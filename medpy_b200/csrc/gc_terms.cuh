@@ -131,8 +131,10 @@ __constant__ double EXPN_C[14] = {
 
 __device__ __forceinline__ double exp_neg(double t)
 {
-    if (!(t <= 745.2)) return (t != t) ? t : 0.0;
-    const double y = -t;
+    // branch-free: the three independent evaluations a voxel needs (+z, +y, +x pair) can be interleaved by the scheduler,
+    // which hides the latency of the dependent DFMA chain.  Out-of-range arguments are computed on a clamped value and
+    // selected away at the end.
+    const double y = fmax(-t, -800.0);                       // NaN -> -800 here, restored by the last select
     const double n = rint(__dmul_rn(y, 1.4426950408889634));
     double r = __fma_rn(-n, 6.93147180369123816490e-01, y);
     r = __fma_rn(-n, 1.90821492927058770002e-10, r);
@@ -140,8 +142,12 @@ __device__ __forceinline__ double exp_neg(double t)
 #pragma unroll
     for (int k = 12; k >= 0; --k) p = __fma_rn(p, r, EXPN_C[k]);
     const int ni = (int)n;
-    if (ni >= -1020) return __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
-    return ldexp(p, ni);
+    const bool tiny = ni < -1020;                             // result (nearly) subnormal: scale in two exact/rounded-once steps
+    const unsigned adj = (unsigned)(tiny ? ni + 64 : ni);
+    double res = __hiloint2double((int)((unsigned)__double2hiint(p) + (adj << 20)), __double2loint(p));
+    res = __dmul_rn(res, tiny ? 5.42101086242752217004e-20 : 1.0);     // 2^-64: one rounding, like ldexp
+    res = (t <= 745.2) ? res : 0.0;
+    return (t != t) ? t : res;
 }
 
 // FN >= 0 fixes the term at compile time (the specialised kernels of the common cases), FN < 0 reads it from P
