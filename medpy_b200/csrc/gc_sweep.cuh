@@ -20,7 +20,7 @@
 #include "gc_tiles.cuh"
 #include "gc_tiles4.cuh"
 
-#define SWEEP_UNROLL 8
+#define SWEEP_UNROLL 16
 
 __device__ __forceinline__ int sweep_inc(int h) { return h >= MGC_HINF ? MGC_HINF : h + 1; }
 
