@@ -37,7 +37,28 @@ import sys
 import tempfile
 import time
 
-import numpy
+
+
+def _cpu_quota():
+    """CPUs this process may actually use: the cgroup quota (cpu.max) when there is one, else the affinity mask.  The GPU box
+    shows 128 logical CPUs to a 16-CPU container; numpy / torch worker pools sized for 128 spin past the quota and the
+    kernel's CFS throttling then stalls EVERY thread of the process for up to 100 ms (measured: e2e steps of 27 ms with
+    outliers of 80-290 ms), so the pools are capped before those libraries are imported."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
+CPU_QUOTA = _cpu_quota()
+for _k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+    os.environ.setdefault(_k, str(max(1, min(8, CPU_QUOTA // 2))))
+
+import numpy  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -173,7 +194,7 @@ def cpu_baseline_obj(r, size, workload_size):
                   "numpy terms %.2fs + C++ graph fill %.2fs + BK maxflow() %.2fs + read-out %.2fs"
                   % (size, "all" if frac >= 1.0 else "1/%d" % round(1.0 / frac), r["terms_s"], r["fill_s"], r["maxflow_s"], r["readout_s"]),
         "maxflow_only_value": r["n"] / max(r["maxflow_s"], 1e-9) / 1e6,
-        "host_cores_available": os.cpu_count(),
+        "host_cores_available": os.cpu_count(), "host_cpu_quota": CPU_QUOTA,
     }
 
 
@@ -290,6 +311,7 @@ def run_gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    torch.set_num_threads(max(1, min(8, CPU_QUOTA // max(1, min(world, 8)) // 2 or 1)))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     size = args.size

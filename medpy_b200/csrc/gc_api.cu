@@ -191,7 +191,7 @@ struct mgc_graph {
     bool use_sweeps = true;
     int sweep_frac = 8;                // sweep when pending tiles > ntiles / sweep_frac
     int sweep_rounds_max = 4;
-    int sweep_done_frac = 64;          // hand over to the worklist BFS when violating tiles <= ntiles / sweep_done_frac
+    int sweep_done_frac = 16;          // hand over to the worklist BFS when violating tiles <= ntiles / sweep_done_frac (measured best on configs 2 / 4)
 
     // tuning
     int sweeps_per_round = 32;

@@ -92,6 +92,28 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
     const bool use_max = USE_MAX >= 0 ? (USE_MAX != 0) : (P.use_max != 0);
     const bool spacing = SPACING >= 0 ? (SPACING != 0) : (P.inv_spacing_on != 0.0);
 
+    const int gy = y0 + ly, gx = x0 + lx;
+    const bool col_in = gy < L.dim[1] && gx < L.dim[2];
+    // t-link inputs of one voxel (probability, marker flags), fetched ONE z-step ahead of their use: ncu showed the loop
+    // stalled on these global loads (long scoreboard 7 of 15 cycles per issue) when they were read where they are needed
+    struct TIn { double p; unsigned fb; };
+    auto fetch = [&](int lz) -> TIn {
+        TIn r{0.0, 0u};
+        const int gz = z0 + lz;
+        if (!(col_in && gz < L.dim[0])) return r;
+        const unsigned v = (unsigned)gz * L.stride[0] + (unsigned)gy * L.stride[1] + (unsigned)gx;
+        if (A.prob) r.p = A.prob_f64 ? reinterpret_cast<const double*>(A.prob)[v] : (double)reinterpret_cast<const float*>(A.prob)[v];
+        if (A.fg_bits || A.bg_bits) {
+            if (A.fg_bits) r.fb |= (A.fg_bits[v >> 5] >> (v & 31u)) & 1u;
+            if (A.bg_bits) r.fb |= ((A.bg_bits[v >> 5] >> (v & 31u)) & 1u) << 1;
+        } else {
+            if (A.fg && A.fg[v]) r.fb |= 1u;
+            if (A.bg && A.bg[v]) r.fb |= 2u;
+        }
+        return r;
+    };
+    TIn cur = fetch(0);            // in flight while the image block is staged
+
     // ---- stage the image block with halo: local (hz, hy, hx) <-> global (z0 - 1 + hz, y0 - 1 + hy, x0 - 1 + hx) ----
     // TMA: the box starts at a non-negative, 16-byte aligned x (see BuildBox) and at non-negative y / z: blocks on a low
     // face start at 0 and the shared-memory index is shifted instead -- the halo cells in front of the lattice are never
@@ -122,8 +144,6 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
         __syncthreads();
     }
 
-    const int gy = y0 + ly, gx = x0 + lx;
-    const bool col_in = gy < L.dim[1] && gx < L.dim[2];
     const bool has_py = gy + 1 < L.dim[1], has_px = gx + 1 < L.dim[2];
     const double sp_z = spacing ? P.spacing[0] : 1.0, sp_y = spacing ? P.spacing[1] : 1.0, sp_x = spacing ? P.spacing[2] : 1.0;
     // (cells in front of the lattice do not exist when the box was clamped: their index is clamped too, the value is
@@ -167,6 +187,8 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
         double* wyb = s_wy + (lz & 1) * 9 * 32;
         double* wxb = s_wx + (lz & 1) * 8 * 33;
         const int hz = lz + 1;
+        TIn nxt{0.0, 0u};
+        if (lz + 1 < BUILD_TZ) nxt = fetch(lz + 1);
         // the three forward pair weights of this voxel: independent, branch-free evaluations
         const double a = build_val<E>(at(hz, ly + 1, lx + 1), use_max);
         const double wz = pair_w(a, at(hz + 1, ly + 1, lx + 1), pin && gz + 1 < L.dim[0], sp_z);
@@ -188,25 +210,17 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
             if (A.prob) {
                 double s, t;
                 if (A.compute_f32) {
-                    const float p = A.prob_f64 ? (float)reinterpret_cast<const double*>(A.prob)[v] : reinterpret_cast<const float*>(A.prob)[v];
+                    const float p = (float)cur.p;          // exact: the map is float32 when its products are
                     const float af = (float)A.alpha;
                     s = (double)__fmul_rn(p, af);
                     t = (double)__fmul_rn(__fsub_rn(1.0f, p), af);
                 } else {
-                    const double p = A.prob_f64 ? reinterpret_cast<const double*>(A.prob)[v] : (double)reinterpret_cast<const float*>(A.prob)[v];
-                    s = __dmul_rn(p, A.alpha);
-                    t = __dmul_rn(__dsub_rn(1.0, p), A.alpha);
+                    s = __dmul_rn(cur.p, A.alpha);
+                    t = __dmul_rn(__dsub_rn(1.0, cur.p), A.alpha);
                 }
                 mm = add_tweights_dev(tr, s, t);
             }
-            bool f, b;
-            if (A.fg_bits || A.bg_bits) {
-                f = A.fg_bits && ((A.fg_bits[v >> 5] >> (v & 31u)) & 1u);
-                b = A.bg_bits && ((A.bg_bits[v >> 5] >> (v & 31u)) & 1u);
-            } else {
-                f = A.fg && A.fg[v];
-                b = A.bg && A.bg[v];
-            }
+            const bool f = (cur.fb & 1u) != 0, b = (cur.fb & 2u) != 0;
             if (f) mm = __dadd_rn(mm, add_tweights_dev(tr, 65535.0, 0.0));
             if (b) mm = __dadd_rn(mm, add_tweights_dev(tr, 0.0, 65535.0));
             const bool own = gz >= L.own0 && gz < L.own1;
@@ -231,6 +245,7 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
             if (e > 0) exc_any = 1u;
         }
         wz_back = wz;
+        cur = nxt;
         // the planes of this step are read above; the next step writes the other buffer, the one after waits at its barrier
     }
 

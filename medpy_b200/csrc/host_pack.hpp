@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <thread>
 #include <vector>
 #if defined(__x86_64__)
@@ -55,7 +57,17 @@ struct MarkerPacker {
         src[0] = fg; src[1] = bg; dst[0] = fgb; dst[1] = bgb;
         nblocks = done.size();
         for (auto& d : done) d.store(0);
+        // worker count: at most 8, and no more than the container's CPU quota allows (hardware_concurrency() reports the
+        // machine's logical CPUs; oversubscribing a cgroup quota gets every thread of the process throttled)
         unsigned nt = std::thread::hardware_concurrency();
+        if (const char* e = std::getenv("MEDPY_GC_PACK_THREADS")) { if (std::atoi(e) > 0) nt = (unsigned)std::atoi(e); }
+        else {
+            if (FILE* f = std::fopen("/sys/fs/cgroup/cpu.max", "r")) {
+                long long q = 0, per = 0;
+                if (std::fscanf(f, "%lld %lld", &q, &per) == 2 && q > 0 && per > 0) { const unsigned lim = (unsigned)(q / per / 2); if (lim >= 1 && lim < nt) nt = lim; }
+                std::fclose(f);
+            }
+        }
         nt = nt < 2 ? 1 : (nt > 8 ? 8 : nt);
         if (nblocks < nt) nt = (unsigned)nblocks;
         for (unsigned i = 0; i < nt; ++i) workers.emplace_back([this] { run(); });
