@@ -1306,8 +1306,25 @@ bool make_image_map(mgc_graph* g, const void* img, int dtype, CUtensorMap* out)
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// rank-3 tensor map of a C-contiguous array over the local lattice with an 8 x 8 x 32 box (probability map, marker bytes)
+bool make_block_map(mgc_graph* g, const void* ptr, int dtype, CUtensorMap* out)
+{
+    tmap_encode_fn encode = tensor_map_encoder();
+    if (!encode || !ptr) return false;
+    const size_t es = dtype_size(dtype);
+    const cuuint64_t X = (cuuint64_t)g->L.dim[2], Y = (cuuint64_t)g->L.dim[1], Z = (cuuint64_t)g->L.dim[0];
+    if ((X * es) % 16 || ((uintptr_t)ptr & 15)) return false;
+    const CUtensorMapDataType dt = dtype == MGC_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : (dtype == MGC_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8);
+    const cuuint64_t dims[3] = {X, Y, Z};
+    const cuuint64_t strides[2] = {X * es, X * Y * es};
+    const cuuint32_t box[3] = {BUILD_TX, BUILD_TY, BUILD_TZ};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return encode(out, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <typename E, int FN, int USE_MAX, int SPACING>
-int build_launch_inst(mgc_graph* g, const CUtensorMap& imap, const BuildArgs& A, const BoundaryParams& P, int nz_layers)
+int build_launch_inst(mgc_graph* g, const BuildMaps& imap, const BuildArgs& A, const BoundaryParams& P, int nz_layers)
 {
     auto kern = k_build_tile<E, double, FN, USE_MAX, SPACING>;
     const size_t smem = build_smem_bytes<E>();
@@ -1322,7 +1339,7 @@ int build_launch_inst(mgc_graph* g, const CUtensorMap& imap, const BuildArgs& A,
 }
 
 template <typename E>
-int build_launch(mgc_graph* g, const CUtensorMap& imap, const BuildArgs& A, const BoundaryParams& P, int nz_layers)
+int build_launch(mgc_graph* g, const BuildMaps& imap, const BuildArgs& A, const BoundaryParams& P, int nz_layers)
 {
     if constexpr (!std::is_integral<E>::value) {
         if (P.fn == 1 && P.inv_spacing_on == 0.0) {
@@ -1333,7 +1350,7 @@ int build_launch(mgc_graph* g, const CUtensorMap& imap, const BuildArgs& A, cons
     return build_launch_inst<E, -1, -1, -1>(g, imap, A, P, nz_layers);
 }
 
-int build_launch_dtype(mgc_graph* g, int dtype, const CUtensorMap& imap, const BuildArgs& A, const BoundaryParams& P, int nz_layers)
+int build_launch_dtype(mgc_graph* g, int dtype, const BuildMaps& imap, const BuildArgs& A, const BoundaryParams& P, int nz_layers)
 {
     switch (dtype) {
         case MGC_F32: return build_launch<float>(g, imap, A, P, nz_layers);
@@ -1774,9 +1791,19 @@ int mgc_build_voxel_graph(mgc_graph* g, const mgc_voxel_terms* t)
     A.alpha = t->alpha;
     if (has_bits) { A.fg_bits = (const unsigned*)d_fg; A.bg_bits = (const unsigned*)d_bg; }
     else { A.fg = (const uint8_t*)d_fg; A.bg = (const uint8_t*)d_bg; }
-    CUtensorMap imap{};
-    A.use_tma = make_image_map(g, d_img, t->image->dtype, &imap) ? 1 : 0;
+    BuildMaps imap{};
+    A.use_tma = make_image_map(g, d_img, t->image->dtype, &imap.img) ? 1 : 0;
     if (const char* e = getenv("MEDPY_GC_BUILD_TMA")) if (atoi(e) == 0) A.use_tma = 0;
+    int tin_tma = A.use_tma;                 // t-link inputs through TMA as well (MEDPY_GC_BUILD_TMA=2: image only)
+    if (const char* e = getenv("MEDPY_GC_BUILD_TMA")) if (atoi(e) == 2) tin_tma = 0;
+    if (tin_tma) {
+        if (d_prob && make_block_map(g, d_prob, t->prob->dtype, &imap.prob)) A.tma_prob = 1;
+        if (!has_bits) {
+            if (d_fg && make_block_map(g, d_fg, MGC_U8, &imap.fg)) A.tma_mark |= 1;
+            if (d_bg && make_block_map(g, d_bg, MGC_U8, &imap.bg)) A.tma_mark |= 2;
+        }
+    }
+    if (const char* e = getenv("MEDPY_GC_BUILD_DBG")) A.dbg = atoi(e);
 
     CK(cudaMemsetAsync(g->d_tcount, 0, 256, g->stream));
     CK(cudaMemsetAsync(g->d_flags, 0, sizeof(int), g->stream));

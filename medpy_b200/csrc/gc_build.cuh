@@ -34,12 +34,19 @@
 // start along the innermost axis is negative or not 16-byte aligned, so the box starts BUILD_PAD = 16 / sizeof(E)
 // elements in front of the block (x0 is a multiple of 32) instead of 1, or at 0 for the blocks on the low x face; the
 // extent covers pad + 32 + 1 elements, rounded up to a multiple of 16 bytes.
+// shared-memory offset of the staged t-link inputs: behind image block, weight planes, barrier, flags, reduction scratch
+#define BUILD_TIN_OFFSET(img_pad) ((((img_pad) + (2 * 9 * 32 + 2 * 8 * 33 + 8 * 32 + 8 * 8) * 8 + 8 + 32 + 64) + 127) / 128 * 128)
 template <typename E> struct BuildBox {
     static constexpr int PAD = 16 / (int)sizeof(E);
     static constexpr int BX = (PAD + 33 + PAD - 1) / PAD * PAD;      // f32 40, f64 36, u8 64, i16 48, i32 40
 };
 #define BUILD_HY 10
 #define BUILD_HZ 10
+
+// tensor maps of one build: image (halo box), probability map and the two marker volumes (8 x 8 x 32 blocks)
+struct BuildMaps {
+    CUtensorMap img, prob, fg, bg;
+};
 
 struct BuildArgs {
     const void* img;           // C-contiguous image over the local lattice (device)
@@ -52,7 +59,10 @@ struct BuildArgs {
     const unsigned* fg_bits;   // ... or bit-packed (bit v & 31 of word v >> 5), used when fg/bg are nullptr
     const unsigned* bg_bits;
     int use_tma;               // image block staged by TMA (else plain loads)
+    int tma_prob;              // probability block (8 x 8 x 32) staged by TMA into shared memory
+    int tma_mark;              // fg / bg byte blocks staged by TMA (bit 0: fg, bit 1: bg)
     int z_tile0;               // first z tile layer of this launch (chunked builds)
+    int dbg;                   // diagnostics (MEDPY_GC_BUILD_DBG): 1 = do not load the probability map (constant 0.3)
 };
 
 template <typename E>
@@ -71,7 +81,7 @@ __device__ __forceinline__ double build_pair(const BoundaryParams& P, double a, 
 
 template <typename E, typename T, int FN, int USE_MAX, int SPACING>
 __global__ void __launch_bounds__(BUILD_THREADS)
-k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMap imap, BuildArgs A, BoundaryParams P,
+k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ BuildMaps maps, BuildArgs A, BoundaryParams P,
              int* __restrict__ bad, double* __restrict__ partials, int* __restrict__ rflag, WorkList rl,
              int* __restrict__ pflag, WorkList pl0, WorkList pl1)
 {
@@ -85,6 +95,11 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(s_wx + 2 * 8 * 33 + 8 * 32 + 8 * 8);
     int* s_flags = reinterpret_cast<int*>(bar + 1);                              // [4] needs, [4] has excess
     double* s_red = reinterpret_cast<double*>(s_flags + 8);                      // [8] block reduction
+    // TMA-staged t-link inputs (ncu + A/B runs: reading them with LDG from inside the store-saturated loop cost 0.7 ms of
+    // a 3.0 ms launch at 512^3; the async-proxy copies are free of the LSU queue)
+    unsigned char* s_prob = smem_raw + BUILD_TIN_OFFSET(IMG_PAD);                // [8][8][32] float or double, 128-B aligned
+    unsigned char* s_fg = s_prob + BUILD_TZ * BUILD_TY * BUILD_TX * 8;           // [8][8][32] bytes
+    unsigned char* s_bg = s_fg + BUILD_TZ * BUILD_TY * BUILD_TX;
 
     const int tid = threadIdx.x;
     const int lx = tid & 31, ly = tid >> 5;
@@ -102,17 +117,23 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
         const int gz = z0 + lz;
         if (!(col_in && gz < L.dim[0])) return r;
         const unsigned v = (unsigned)gz * L.stride[0] + (unsigned)gy * L.stride[1] + (unsigned)gx;
-        if (A.prob) r.p = A.prob_f64 ? reinterpret_cast<const double*>(A.prob)[v] : (double)reinterpret_cast<const float*>(A.prob)[v];
+        const int si = (lz * BUILD_TY + ly) * BUILD_TX + lx;          // index inside the staged 8 x 8 x 32 blocks
+        if (A.prob) {
+            if (A.tma_prob) r.p = A.prob_f64 ? reinterpret_cast<const double*>(s_prob)[si] : (double)reinterpret_cast<const float*>(s_prob)[si];
+            else r.p = (A.dbg & 1) ? 0.3 : (A.prob_f64 ? reinterpret_cast<const double*>(A.prob)[v] : (double)reinterpret_cast<const float*>(A.prob)[v]);
+        }
         if (A.fg_bits || A.bg_bits) {
             if (A.fg_bits) r.fb |= (A.fg_bits[v >> 5] >> (v & 31u)) & 1u;
             if (A.bg_bits) r.fb |= ((A.bg_bits[v >> 5] >> (v & 31u)) & 1u) << 1;
         } else {
-            if (A.fg && A.fg[v]) r.fb |= 1u;
-            if (A.bg && A.bg[v]) r.fb |= 2u;
+            if (A.fg && ((A.tma_mark & 1) ? s_fg[si] : A.fg[v])) r.fb |= 1u;
+            if (A.bg && ((A.tma_mark & 2) ? s_bg[si] : A.bg[v])) r.fb |= 2u;
         }
         return r;
     };
-    TIn cur = fetch(0);            // in flight while the image block is staged
+    const bool staged_tin = A.use_tma && ((A.prob && A.tma_prob) || A.tma_mark);
+    TIn cur{0.0, 0u};
+    if (!staged_tin) cur = fetch(0);          // global loads: in flight while the image block is staged
 
     // ---- stage the image block with halo: local (hz, hy, hx) <-> global (z0 - 1 + hz, y0 - 1 + hy, x0 - 1 + hx) ----
     // TMA: the box starts at a non-negative, 16-byte aligned x (see BuildBox) and at non-negative y / z: blocks on a low
@@ -126,11 +147,17 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
         if (tid == 0) {
             mbar_init(bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            mbar_expect_tx(bar, (unsigned)IMG_BYTES);
-            tma_load_3d(s_img, &imap, bar, x0 - 1 - cx, y0 - 1 - cy, z0 - 1 - cz);
+            const unsigned pbytes = (A.prob && A.tma_prob) ? (unsigned)(BUILD_TZ * BUILD_TY * BUILD_TX * (A.prob_f64 ? 8 : 4)) : 0u;
+            const unsigned mbytes = (unsigned)(BUILD_TZ * BUILD_TY * BUILD_TX);
+            mbar_expect_tx(bar, (unsigned)IMG_BYTES + pbytes + ((A.tma_mark & 1) ? mbytes : 0u) + ((A.tma_mark & 2) ? mbytes : 0u));
+            tma_load_3d(s_img, &maps.img, bar, x0 - 1 - cx, y0 - 1 - cy, z0 - 1 - cz);
+            if (pbytes) tma_load_3d(s_prob, &maps.prob, bar, x0, y0, z0);
+            if (A.tma_mark & 1) tma_load_3d(s_fg, &maps.fg, bar, x0, y0, z0);
+            if (A.tma_mark & 2) tma_load_3d(s_bg, &maps.bg, bar, x0, y0, z0);
         }
         __syncthreads();
         mbar_wait(bar, 0u);
+        if (staged_tin) cur = fetch(0);
     } else {
         const E* img = reinterpret_cast<const E*>(A.img);
         for (int i = tid; i < BUILD_HZ * BUILD_HY * 34; i += BUILD_THREADS) {
@@ -289,8 +316,8 @@ k_build_tile(Lattice L, Tiles TL, State<T> S, const __grid_constant__ CUtensorMa
 template <typename E>
 constexpr size_t build_smem_bytes()
 {
-    return (size_t)((BUILD_HZ * BUILD_HY * BuildBox<E>::BX * sizeof(E) + 127) / 128 * 128) + (2 * 9 * 32 + 2 * 8 * 33 + 8 * 32 + 8 * 8) * sizeof(double) + 8 + 8 * sizeof(int) +
-           8 * sizeof(double) + 64;
+    return (size_t)BUILD_TIN_OFFSET((BUILD_HZ * BUILD_HY * BuildBox<E>::BX * (int)sizeof(E) + 127) / 128 * 128) +
+           (size_t)BUILD_TZ * BUILD_TY * BUILD_TX * (8 + 1 + 1);
 }
 
 // ---------------------------------------------------------------------------------------------------
