@@ -430,6 +430,10 @@ def run_extras_single(torch, peak):
                          "push_sweeps": st["push_sweeps"], "global_relabels": st["global_relabels"], "relabel_sweeps": st["relabel_sweeps"],
                          "ms_build": st["ms_boundary"], "ms_relabel": st["ms_relabel"], "ms_push": st["ms_push"], "ms_solve": st["ms_solve"],
                          "gen_s": gen_s, "sigma": vol["sigma"]}
+            if name.startswith("config5"):
+                ref5 = committed_mask_hash("config5_1024")
+                out[name]["single_gpu_mask_sha256_committed"] = ref5
+                out[name]["mask_matches_committed"] = (out[name]["mask_sha256"] == ref5) if ref5 else None
             del d_mask, mask, vol
             torch.cuda.empty_cache()
             if big:

@@ -425,7 +425,7 @@ def bench_config5(args, rank, world, local_rank, shape=(1024, 1024, 1024)):
     """BASELINE config 5: 1024^3 fp32, boundary_difference_exponential, z-slab partitioned over the ranks.  One warm-up
     and two timed steps; the gathered mask is hashed on rank 0 (compare with the single-GPU run's config.extra)."""
     import torch
-    from bench import measured_peak, sha256_of, UNIT  # noqa
+    from bench import measured_peak, sha256_of, committed_mask_hash, UNIT  # noqa
     try:
         r = _slab_resident(shape, rank, world, local_rank, False, 2, 1)
     except Exception as exc:
@@ -438,6 +438,9 @@ def bench_config5(args, rank, world, local_rank, shape=(1024, 1024, 1024)):
            "hbm_read_roofline_frac": (n * 7 / (r["ms"] * 1e-3)) / (peak * 1e9 * world), "n_gpus": world,
            "push_passes": s.stats["push_passes"], "global_relabels": s.stats["global_relabels"], "exchanges": s.stats["exchanges"],
            "sigma": r["vol"]["sigma"]}
+    ref5 = committed_mask_hash("config5_1024") if tuple(shape) == (1024, 1024, 1024) else None
+    out["single_gpu_mask_sha256_committed"] = ref5
+    out["mask_matches_single_gpu"] = (out["mask_sha256"] == ref5) if (ref5 and rank == 0) else None
     del r
     torch.cuda.empty_cache()
     return out

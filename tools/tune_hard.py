@@ -7,7 +7,7 @@ import torch
 from medpy_b200 import synthetic
 from medpy_b200.graphcut.device import graph_from_device_arrays
 
-CONFIGS = {"2": ((256, 256, 256), "difference_exponential", False), "4": ((256, 256, 128, 4), "maximum_exponential", True),
+CONFIGS = {"3": ((512, 512, 512), "difference_exponential", False),"2": ((256, 256, 256), "difference_exponential", False), "4": ((256, 256, 128, 4), "maximum_exponential", True),
            "2h": ((512, 512, 512), "difference_exponential", False), "4s": ((64, 64, 32, 4), "maximum_exponential", True)}
 VARIANTS = [
     {},
@@ -19,19 +19,21 @@ VARIANTS = [
 ]
 for key in (sys.argv[1:] or ["2"]):
     shape, boundary, fourd = CONFIGS[key]
-    vol = synthetic.multispectral_volume(shape, seed=0) if fourd else synthetic.two_blob_volume(shape, seed=0, with_prob=False)
+    vol = synthetic.multispectral_volume(shape, seed=0) if fourd else synthetic.two_blob_volume(shape, seed=0, with_prob=(key == "3"))
+    d_prob = torch.from_numpy(vol["prob"]).cuda() if key == "3" else None
+    variants = VARIANTS if key != "3" else [{}, {"MEDPY_GC_PASSES0": 2}, {"MEDPY_GC_PASSES0": 3}, {"MEDPY_GC_PASSES0": 2, "MEDPY_GC_ITERS": 8}, {"MEDPY_GC_ITERS": 8}, {"MEDPY_GC_ITERS": 6}, {"MEDPY_GC_PASSES0": 4}]
     d_img = torch.from_numpy(vol["image"]).cuda()
     d_fg = torch.from_numpy(vol["fg"].view(numpy.uint8)).cuda()
     d_bg = torch.from_numpy(vol["bg"].view(numpy.uint8)).cuda()
     ref = None
-    for var in VARIANTS:
+    for var in variants:
         for k in ("MEDPY_GC_ITERS", "MEDPY_GC_SWEEP_ROUNDS", "MEDPY_GC_SWEEP_DONE_FRAC", "MEDPY_GC_PASSES0", "MEDPY_GC_SWEEP", "MEDPY_GC_SWEEP_FRAC"):
             os.environ.pop(k, None)
         for k, v in var.items():
             os.environ[k] = str(v)
         best = None
         for rep in range(3):
-            g = graph_from_device_arrays(d_fg, d_bg, image=d_img, boundary=boundary, sigma=vol["sigma"])
+            g = graph_from_device_arrays(d_fg, d_bg, image=d_img, boundary=boundary, sigma=vol["sigma"], prob=d_prob, alpha=vol.get("alpha"))
             e = g.maxflow()
             st = g.stats()
             if best is None or st["ms_solve"] < best["ms_solve"]:
