@@ -188,6 +188,8 @@ struct mgc_graph {
     int passes0 = 1, passes_max = 32;  // two-colour passes per round: starts at passes0, at most doubles per round
     // directional line sweeps in front of the worklist BFS (gc_sweep.cuh): used when more than 1/sweep_frac of the
     // tiles are waiting for labels (hard instances: the sink is far from most of the lattice)
+    bool skip_first_test = true;       // MEDPY_GC_FIRST_TEST=1 restores the stop test of the first round
+    int sweep_mode = -1;               // decided at the first relabel of a solve: 1 = hard instance (sweep at every relabel), 0 = worklist BFS only
     bool use_sweeps = true;
     int sweep_frac = 8;                // sweep when pending tiles > ntiles / sweep_frac
     int sweep_rounds_max = 4;
@@ -626,11 +628,12 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
     for (auto& ev : g->ev_chunk) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto& ev : g->ev_terms) cudaEventCreate(&ev);
     if (const char* f0 = getenv("MEDPY_GC_DEBUG")) g->debug_checks = atoi(f0) != 0;
+    if (const char* f3 = getenv("MEDPY_GC_FIRST_TEST")) g->skip_first_test = atoi(f3) == 0;
     if (const char* f1 = getenv("MEDPY_GC_FUSE")) g->fuse_build = atoi(f1) != 0;
     if (const char* f2 = getenv("MEDPY_GC_CHUNKS")) if (atoi(f2) > 0) g->build_chunks = atoi(f2);
     cudaEventCreateWithFlags(&g->ev_bad, cudaEventDisableTiming);
     for (auto& ev : g->ev_b) cudaEventCreate(&ev);
-    if (cudaHostAlloc((void**)&g->h_bad, sizeof(int), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); g->h_bad = nullptr; }
+    if (cudaHostAlloc((void**)&g->h_bad, 64, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); g->h_bad = nullptr; }   // [0] weight verdict, [2..3] active count
     if (const char* s1 = getenv("MEDPY_GC_SWEEPS")) g->sweeps_per_round = atoi(s1) > 0 ? atoi(s1) : g->sweeps_per_round;
     if (const char* s2 = getenv("MEDPY_GC_RELAX_BATCH")) g->relax_batch = atoi(s2) > 0 ? atoi(s2) : g->relax_batch;
     g->st.n_voxels = (int64_t)n;
@@ -843,6 +846,7 @@ int init_tiles(mgc_graph* g)
     g->state_init = true;
     g->labels_fresh = true;
     g->rl_cur = 0;
+    g->sweep_mode = -1;
     return MGC_OK;
 }
 
@@ -912,10 +916,13 @@ int relabel_sweep_round(mgc_graph* g, int* pending)
 int relabel_tiles_run(mgc_graph* g, int* any, bool want_any = true)
 {
     *any = 0;
-    if (g->use_sweeps && g->use_tiles && g->TL.ntiles >= 64) {
+    if (g->use_sweeps && g->use_tiles && g->TL.ntiles >= 64 && g->sweep_mode != 0) {
         int pending = 0;
         int rc = read_tcount(g, g->rl_cur, &pending);
         if (rc) return rc;
+        // one decision per solve (one host synchronisation): an instance whose first relabel has to label most of the
+        // lattice is a hard one at every later relabel too, an easy one (regional term: most voxels own a sink link) never is
+        if (g->sweep_mode < 0) g->sweep_mode = pending > g->TL.ntiles / g->sweep_frac ? 1 : 0;
         if (pending > g->TL.ntiles / g->sweep_frac) {
             *any = 1;
             int prev = g->TL.ntiles + 1;
@@ -969,22 +976,6 @@ int relabel_tiles_run(mgc_graph* g, int* any, bool want_any = true)
     return MGC_OK;
 }
 
-int relabel_tiles(mgc_graph* g)
-{
-    Nvtx range("mgc:global_relabel");
-    cudaEventRecord(g->ev[2], g->stream);
-    int rc = relabel_tiles_begin(g);
-    if (rc) return rc;
-    int any = 0;
-    rc = relabel_tiles_run(g, &any);
-    if (rc) return rc;
-    cudaEventRecord(g->ev[3], g->stream);
-    CK(cudaEventSynchronize(g->ev[3]));
-    { float ms = 0; cudaEventElapsedTime(&ms, g->ev[2], g->ev[3]); g->st.ms_relabel += ms; }
-    g->st.global_relabels++;
-    return MGC_OK;
-}
-
 // one colour: consume its current list; still-active tiles go to its alternate list, receivers of cross-face flow
 // to the list the other colour consumes next
 int push_color(mgc_graph* g, int color)
@@ -1029,16 +1020,25 @@ int push_tiles(mgc_graph* g, int passes)
 }
 
 // active voxels, counted exactly over the two pending push lists (a superset of the tiles that can hold one)
+int count_active_tiles_enqueue(mgc_graph* g, unsigned long long* dst)
+{
+    CK(cudaMemsetAsync(dst, 0, sizeof(unsigned long long), g->stream));
+    if (g->nd == 4) {
+        for (int color = 0; color < 2; ++color)
+            k_count_active_tiles4<double><<<g->n_ctas * 2, T4_VOX, 0, g->stream>>>(g->L, g->TL4, g->S, pl(g, color, g->pl_sel[color]), dst);
+        g->st.kernel_launches += 2;
+    } else {
+        k_count_active_tiles2<double><<<g->n_ctas * 2, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S, pl(g, 0, g->pl_sel[0]), pl(g, 1, g->pl_sel[1]), dst);
+        g->st.kernel_launches++;
+    }
+    CK(cudaGetLastError());
+    return MGC_OK;
+}
+
 int count_active_tiles(mgc_graph* g, int64_t* out)
 {
-    CK(cudaMemsetAsync(g->d_count, 0, sizeof(unsigned long long), g->stream));
-    for (int color = 0; color < 2; ++color) {
-        if (g->nd == 4)
-            k_count_active_tiles4<double><<<g->n_ctas * 2, T4_VOX, 0, g->stream>>>(g->L, g->TL4, g->S, pl(g, color, g->pl_sel[color]), g->d_count);
-        else
-            k_count_active_tiles<double><<<g->n_ctas * 2, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S, pl(g, color, g->pl_sel[color]), g->d_count);
-    }
-    g->st.kernel_launches += 2;
+    int rc = count_active_tiles_enqueue(g, g->d_count);
+    if (rc) return rc;
     unsigned long long c = 0;
     CK(cudaMemcpyAsync(&c, g->d_count, sizeof(c), cudaMemcpyDeviceToHost, g->stream));
     CK(cudaStreamSynchronize(g->stream));
@@ -1124,30 +1124,80 @@ int solve_tiles(mgc_graph* g)
         g->labels_fresh = false;
         return solve_coop(g, flags, g->passes0, nullptr);
     }
+    // One host synchronisation per round: relabel (reset + BFS), stop test and the previous round's push passes are all
+    // enqueued back to back; the host waits once, reads the active count and the CUDA-event times of both phases and
+    // decides.  The stop test of the FIRST round is skipped (a graph that was just built almost always has active
+    // voxels; if it has none the push pass is a no-op and the next round's test ends the solve).
     int passes = g->passes0;
     int64_t rounds = 0;
+    bool push_open = false;
+    int passes_done = 0;
+    unsigned long long active_fallback = 0;
+    unsigned long long* h_active = g->h_bad ? (unsigned long long*)g->h_bad + 1 : &active_fallback;      // pinned
     for (;;) {
-        const double rel0 = g->st.ms_relabel;
-        rc = relabel_tiles(g);
-        if (rc) return rc;
-        const double t_rel = g->st.ms_relabel - rel0;
-        int64_t active = 0;
-        rc = count_active_tiles(g, &active);
-        if (rc) return rc;
-        if (active == 0) break;
+        cudaEventRecord(g->ev[2], g->stream);
+        {
+            Nvtx range("mgc:global_relabel");
+            rc = relabel_tiles_begin(g);
+            if (rc) return rc;
+            int any = 0;
+            rc = relabel_tiles_run(g, &any, false);
+            if (rc) return rc;
+        }
+        cudaEventRecord(g->ev[3], g->stream);
+        g->st.global_relabels++;
+        const bool test = rounds > 0 || !g->skip_first_test;
+        if (test) {
+            rc = count_active_tiles_enqueue(g, g->d_count);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(h_active, g->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, g->stream));
+        }
+        CK(cudaEventSynchronize(g->ev[3]));
+        if (test) CK(cudaStreamSynchronize(g->stream));
+        float ms = 0;
+        if (g->init_timed) {          // k_init_tile of the per-term path: its events are reused for the push spans below
+            if (cudaEventElapsedTime(&ms, g->ev[4], g->ev[5]) == cudaSuccess) g->st.ms_init = ms;
+            g->init_timed = false;
+        }
+        cudaEventElapsedTime(&ms, g->ev[2], g->ev[3]);
+        const double t_rel = ms;
+        g->st.ms_relabel += ms;
+        double t_pass = 0.0;
+        if (push_open) {
+            cudaEventElapsedTime(&ms, g->ev[4], g->ev[5]);
+            g->st.ms_push += ms;
+            t_pass = ms / (passes_done > 0 ? passes_done : 1);
+            push_open = false;
+            // next round: at most double, and no more push time than one global relabel costs (measured, not guessed):
+            // easy instances keep relabelling often, hard ones (long BFS, cheap passes) push longer between relabels
+            int want = t_pass > 1e-4 ? (int)(t_rel / t_pass + 0.999) : passes * 2;
+            if (want < 1) want = 1;
+            if (want > passes * 2) want = passes * 2;
+            passes = want > g->passes_max ? g->passes_max : want;
+        }
+        if (test) {
+            g->st.active_last = (int64_t)*h_active;
+            if (*h_active == 0ull) break;
+        }
         if (++rounds > g->max_rounds) FAIL(MGC_E_NOCONV, "push-relabel did not converge within the round cap");
-        const double push0 = g->st.ms_push;
         g->iters_now = rounds == 1 ? g->tile_iters_first : g->tile_iters;
-        rc = push_tiles(g, passes);
-        if (rc) return rc;
-        // next round: at most double, and no more push time than one global relabel costs (measured, not guessed):
-        // easy instances keep relabelling often, hard ones (long BFS, cheap passes) push longer between relabels
-        const double t_pass = (g->st.ms_push - push0) / passes;
-        int want = t_pass > 1e-4 ? (int)(t_rel / t_pass + 0.999) : passes * 2;
-        if (want < 1) want = 1;
-        if (want > passes * 2) want = passes * 2;
-        passes = want > g->passes_max ? g->passes_max : want;
+        {
+            Nvtx range("mgc:push_passes");
+            cudaEventRecord(g->ev[4], g->stream);
+            for (int p = 0; p < passes; ++p) {
+                rc = push_color(g, 0);
+                if (rc) return rc;
+                rc = push_color(g, 1);
+                if (rc) return rc;
+            }
+            cudaEventRecord(g->ev[5], g->stream);
+            g->st.push_sweeps += passes;
+            passes_done = passes;
+            push_open = true;
+            CK(cudaGetLastError());
+        }
     }
+    g->init_timed = false;       // ev[4..5] were reused for the push spans
     return MGC_OK;
 }
 
@@ -1871,6 +1921,7 @@ int mgc_build_voxel_graph(mgc_graph* g, const mgc_voxel_terms* t)
     g->host_mask_valid = false;
     g->labels_fresh = true;
     g->rl_cur = 0;
+    g->sweep_mode = -1;
     g->init_timed = false;
     g->st.ms_init = 0.0;
     span.stop(0x17u);
@@ -2214,9 +2265,7 @@ int mgc_slab_count_active_dev(mgc_graph* g, unsigned long long* count_dev)
     CK(cudaSetDevice(g->device));
     CK(cudaMemsetAsync(count_dev, 0, sizeof(unsigned long long), g->stream));
     if (g->use_tiles) {
-        for (int color = 0; color < 2; ++color)
-            k_count_active_tiles<double><<<g->n_ctas * 2, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S, pl(g, color, g->pl_sel[color]), count_dev);
-        g->st.kernel_launches += 2;
+        return count_active_tiles_enqueue(g, count_dev);
     } else {
         k_count_active<double><<<nblocks(g), 256, 0, g->stream>>>(g->L, g->S, count_dev);
         g->st.kernel_launches++;
