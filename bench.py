@@ -488,13 +488,17 @@ def bench_single(vol, args, torch):
     for _ in range(e2e_warm):
         e_e2e, m_e2e = e2e_step()
     torch.cuda.synchronize()
+    per_step = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
+        ts = time.perf_counter()
         e_e2e, m_e2e = e2e_step()
+        per_step.append(1e3 * (time.perf_counter() - ts))
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     e2e = {"value": n * args.steps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(n * 10), "d2h_bytes_per_step": int(n + 8),
-           "ms_per_step": 1e3 * dt / args.steps, "api": "medpy_b200.graphcut.graph_from_voxels -> maxflow -> get_mask",
+           "ms_per_step": 1e3 * dt / args.steps, "step_ms_min_median_max": [min(per_step), float(numpy.median(per_step)), max(per_step)],
+           "api": "medpy_b200.graphcut.graph_from_voxels -> maxflow -> get_mask",
            "energy_matches_resident_run": bool(abs(e_e2e - energy) <= 1e-12 * abs(energy)),
            "mask_matches_resident_run": bool(sha256_of(m_e2e) == mask_hash),
            "timer": "host perf_counter around synchronised steps (the z-chunked H2D uploads and the D2H mask copy are inside)"}

@@ -25,6 +25,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -633,7 +634,9 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
     if (const char* f2 = getenv("MEDPY_GC_CHUNKS")) if (atoi(f2) > 0) g->build_chunks = atoi(f2);
     cudaEventCreateWithFlags(&g->ev_bad, cudaEventDisableTiming);
     for (auto& ev : g->ev_b) cudaEventCreate(&ev);
-    if (cudaHostAlloc((void**)&g->h_bad, 64, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); g->h_bad = nullptr; }   // [0] weight verdict, [2..3] active count
+    // [0] weight verdict, [2..3] active count.  From the pinned pool: cudaHostAlloc / cudaFreeHost per handle (one handle per
+    // graph_from_voxels call) are heavyweight driver calls that synchronise the device
+    { void* hp = nullptr; g->h_bad = (mgc_host_alloc(64, &hp) == MGC_OK) ? (int*)hp : nullptr; }
     if (const char* s1 = getenv("MEDPY_GC_SWEEPS")) g->sweeps_per_round = atoi(s1) > 0 ? atoi(s1) : g->sweeps_per_round;
     if (const char* s2 = getenv("MEDPY_GC_RELAX_BATCH")) g->relax_batch = atoi(s2) > 0 ? atoi(s2) : g->relax_batch;
     g->st.n_voxels = (int64_t)n;
@@ -1486,8 +1489,8 @@ void mgc_destroy(mgc_graph* g)
     if (g->ev_up) cudaEventDestroy(g->ev_up);
     if (g->ev_bad) cudaEventDestroy(g->ev_bad);
     for (auto& ev : g->ev_b) if (ev) cudaEventDestroy(ev);
-    if (g->h_bad) cudaFreeHost(g->h_bad);
-    if (g->h_stat) cudaFreeHost(g->h_stat);
+    if (g->h_bad) mgc_host_free(g->h_bad);
+    if (g->h_stat) mgc_host_free(g->h_stat);
     slab_comm_release(g);
     if (g->up_stream) { cudaStreamSynchronize(g->up_stream); cudaStreamDestroy(g->up_stream); }
     if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
@@ -1802,7 +1805,7 @@ int mgc_build_voxel_graph(mgc_graph* g, const mgc_voxel_terms* t)
         if (t->bg) { rc = stage_input(g, t->bg, 4, &d_bg); if (rc) return rc; }
         if (has_bits) {
             if (t->bits_ready_words && t->bits_mem == MGC_MEM_HOST) {
-                while (*t->bits_ready_words < (int64_t)words) { }
+                while (*t->bits_ready_words < (int64_t)words) std::this_thread::yield();
                 std::atomic_thread_fence(std::memory_order_acquire);
             }
             const uint32_t* src[2] = {t->fg_bits, t->bg_bits};
@@ -1887,7 +1890,7 @@ int mgc_build_voxel_graph(mgc_graph* g, const mgc_voxel_terms* t)
                 const size_t w0 = v0 / 32, w1 = (v0 + nv + 31) / 32;
                 if (t->bits_ready_words) {        // producer thread still packing: wait until this chunk's words exist
                     const int64_t need = (int64_t)(w1 < words ? w1 : words);
-                    while (*t->bits_ready_words < need) { /* spin: packing runs at memory speed, far ahead of PCIe */ }
+                    while (*t->bits_ready_words < need) std::this_thread::yield();   // packing runs at memory speed, far ahead of PCIe
                     std::atomic_thread_fence(std::memory_order_acquire);
                 }
                 if (t->fg_bits) CK(cudaMemcpyAsync((uint32_t*)g->scratch[1].p + w0, t->fg_bits + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, g->up_stream));
@@ -2320,7 +2323,7 @@ int mgc_slab_comm_init(mgc_graph* g, int32_t rank, int32_t world, const void* un
     for (int i = 0; i < 4; ++i) if (!g->msg[i]) { int rc = alloc_buf(g, g->msg_bytes, &p); if (rc) return rc; g->msg[i] = (char*)p; CK(cudaMemsetAsync(p, 0, g->msg_bytes, g->stream)); }
     if (!g->d_stat) { int rc = alloc_buf(g, 64, &p); if (rc) return rc; g->d_stat = (long long*)p; }
     if (!g->d_esum) { int rc = alloc_buf(g, 64, &p); if (rc) return rc; g->d_esum = (double*)p; }
-    if (!g->h_stat) CK(cudaHostAlloc((void**)&g->h_stat, 64, cudaHostAllocDefault));
+    if (!g->h_stat) { void* hp = nullptr; if (mgc_host_alloc(64, &hp) != MGC_OK) FAIL(MGC_E_NOMEM, "pinned host allocation failed"); g->h_stat = (long long*)hp; }
     return MGC_OK;
 }
 
