@@ -270,6 +270,10 @@ int mgc_slab_comm_init(mgc_graph* g, int32_t rank, int32_t world, const void* un
 int mgc_slab_solve(mgc_graph* g, double* energy_total);
 int mgc_slab_solve_stats(const mgc_graph* g, int64_t* exchanges, int64_t* relabel_rounds, int64_t* push_passes,
                          int64_t* global_relabels);
+/* Device milliseconds of the last mgc_slab_solve per phase (CUDA events on the handle's stream): out6[0] local BFS,
+ * [1] border exchanges (pack + ncclSend/ncclRecv + unpack), [2] stop test (count + all-reduce), [3] push passes,
+ * [4] read-out + energy all-reduce, and out6[5] = HOST milliseconds spent blocked in the per-round synchronisations. */
+int mgc_slab_solve_phase_ms(const mgc_graph* g, double* out6);
 
 /* ---- general sparse graphs ----------------------------------------------------- */
 

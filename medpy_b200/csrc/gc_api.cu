@@ -18,6 +18,7 @@
 #include <nvtx3/nvToolsExt.h>
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -211,6 +212,13 @@ struct mgc_graph {
     long long* h_stat = nullptr;       // pinned mirror
     double* d_esum = nullptr;          // energy all-reduce
     int64_t slab_exchanges = 0, slab_relabel_rounds = 0, slab_push_passes = 0, slab_global_relabels = 0;
+    // per-phase device time of the last mgc_slab_solve (CUDA events on the stream, resolved at the end of the solve):
+    // [0] local BFS (reset + relax), [1] border exchanges (pack + NCCL send/recv + unpack), [2] stop test (count + all-reduce),
+    // [3] push passes, [4] read-out + energy all-reduce; [5] = host time blocked in stream synchronisations (ms)
+    std::vector<cudaEvent_t> ph_events;
+    std::vector<int> ph_kind;
+    size_t ph_used = 0;
+    double slab_phase_ms[6] = {0, 0, 0, 0, 0, 0};
 
     mgc_stats st{};
     std::string err;
@@ -1294,10 +1302,34 @@ int slab_comm_poll(mgc_graph* g)
     return MGC_OK;
 }
 
+// phase spans of the slab solve: begin / end record an event pair on the stream; resolved once the solve is over
+void phase_begin(mgc_graph* g, int kind)
+{
+    if (g->ph_used + 2 > g->ph_events.size()) { g->ph_events.resize(g->ph_used + 2, nullptr); }
+    for (int i = 0; i < 2; ++i) if (!g->ph_events[g->ph_used + i]) cudaEventCreate(&g->ph_events[g->ph_used + i]);
+    cudaEventRecord(g->ph_events[g->ph_used], g->stream);
+    g->ph_kind.push_back(kind);
+}
+void phase_end(mgc_graph* g)
+{
+    cudaEventRecord(g->ph_events[g->ph_used + 1], g->stream);
+    g->ph_used += 2;
+}
+void phase_resolve(mgc_graph* g)
+{
+    for (size_t i = 0; i + 1 < g->ph_used; i += 2) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, g->ph_events[i], g->ph_events[i + 1]) == cudaSuccess) g->slab_phase_ms[g->ph_kind[i / 2]] += ms;
+    }
+    g->ph_used = 0;
+    g->ph_kind.clear();
+}
+
 // one border exchange: pack -> grouped send/recv with both neighbours -> unpack, all enqueued on the handle's stream
 int slab_exchange(mgc_graph* g, long long* changed_dev)
 {
     Nvtx range("mgc:slab_exchange");
+    phase_begin(g, 1);
     NcclApi& N = nccl_api();
     const unsigned P = g->L.plane;
     const unsigned nb = (P + 255u) / 256u;
@@ -1323,7 +1355,9 @@ int slab_exchange(mgc_graph* g, long long* changed_dev)
     const int32_t* h_hi = have[1] ? (const int32_t*)g->msg[3] : nullptr;
     const double* f_hi = have[1] ? (const double*)(g->msg[3] + g->msg_h_bytes) : nullptr;
     g->slab_exchanges++;
-    return mgc_slab_unpack(g, h_lo, f_lo, h_hi, f_hi, (int32_t*)changed_dev);
+    const int rc_unpack = mgc_slab_unpack(g, h_lo, f_lo, h_hi, f_hi, (int32_t*)changed_dev);
+    phase_end(g);
+    return rc_unpack;
 }
 
 // ---- fused graph build (gc_build.cuh) ------------------------------------------------------------------
@@ -1489,6 +1523,7 @@ void mgc_destroy(mgc_graph* g)
     if (g->ev_up) cudaEventDestroy(g->ev_up);
     if (g->ev_bad) cudaEventDestroy(g->ev_bad);
     for (auto& ev : g->ev_b) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : g->ph_events) if (ev) cudaEventDestroy(ev);
     if (g->h_bad) mgc_host_free(g->h_bad);
     if (g->h_stat) mgc_host_free(g->h_stat);
     slab_comm_release(g);
@@ -2340,26 +2375,40 @@ int mgc_slab_solve(mgc_graph* g, double* energy_total)
     int rc = mgc_slab_begin(g);
     if (rc) return rc;
     g->slab_exchanges = g->slab_relabel_rounds = g->slab_push_passes = g->slab_global_relabels = 0;
+    for (double& x : g->slab_phase_ms) x = 0.0;
+    g->ph_used = 0; g->ph_kind.clear();
+    auto timed_sync = [&]() -> cudaError_t {
+        const auto t0 = std::chrono::steady_clock::now();
+        const cudaError_t e = cudaStreamSynchronize(g->stream);
+        g->slab_phase_ms[5] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return e;
+    };
     int passes = g->passes0 > 0 ? g->passes0 : 1;
     const int passes_cap = g->passes_max < 8 ? g->passes_max : 8;
     int64_t rounds = 0;
     for (;;) {
+        phase_begin(g, 0);
         rc = mgc_slab_relabel_begin(g);
+        phase_end(g);
         if (rc) return rc;
         for (;;) {
             CK(cudaMemsetAsync(g->d_stat, 0, 3 * sizeof(long long), g->stream));
             for (int k = 0; k < 2; ++k) {
+                phase_begin(g, 0);
                 rc = mgc_slab_relabel_relax(g, nullptr);
+                phase_end(g);
                 if (rc) return rc;
                 rc = slab_exchange(g, g->d_stat + k);
                 if (rc) return rc;
                 g->slab_relabel_rounds++;
             }
+            phase_begin(g, 2);
             rc = mgc_slab_count_active_dev(g, (unsigned long long*)(g->d_stat + 2));
             if (rc) return rc;
             if (g->comm_world > 1) NK(N.AllReduce(g->d_stat, g->d_stat, 3, ncclInt64, ncclSum, g->comm, g->stream));
             CK(cudaMemcpyAsync(g->h_stat, g->d_stat, 3 * sizeof(long long), cudaMemcpyDeviceToHost, g->stream));
-            CK(cudaStreamSynchronize(g->stream));                     // the one host decision of this round
+            phase_end(g);
+            CK(timed_sync());                                          // the one host decision of this round
             rc = slab_comm_poll(g);
             if (rc) return rc;
             if (g->h_stat[1] == 0) break;
@@ -2368,7 +2417,9 @@ int mgc_slab_solve(mgc_graph* g, double* energy_total)
         if (g->h_stat[2] == 0) break;
         if (++rounds > g->max_rounds) FAIL(MGC_E_NOCONV, "push-relabel did not converge within the round cap");
         for (int p = 0; p < passes; ++p) {
+            phase_begin(g, 3);
             rc = mgc_slab_push(g, 1);
+            phase_end(g);
             if (rc) return rc;
             rc = slab_exchange(g, nullptr);
             if (rc) return rc;
@@ -2377,13 +2428,23 @@ int mgc_slab_solve(mgc_graph* g, double* energy_total)
         passes = passes * 2 > passes_cap ? passes_cap : passes * 2;
     }
     double part = 0.0;
+    phase_begin(g, 4);
     rc = mgc_slab_finish(g, &part);
     if (rc) return rc;
     CK(cudaMemcpyAsync(g->d_esum, &part, sizeof(double), cudaMemcpyHostToDevice, g->stream));
     if (g->comm_world > 1) NK(N.AllReduce(g->d_esum, g->d_esum, 1, ncclFloat64, ncclSum, g->comm, g->stream));
     CK(cudaMemcpyAsync(energy_total, g->d_esum, sizeof(double), cudaMemcpyDeviceToHost, g->stream));
-    CK(cudaStreamSynchronize(g->stream));
+    phase_end(g);
+    CK(timed_sync());
+    phase_resolve(g);
     return slab_comm_poll(g);
+}
+
+int mgc_slab_solve_phase_ms(const mgc_graph* g, double* out6)
+{
+    if (!g || !out6) return MGC_E_ARG;
+    for (int i = 0; i < 6; ++i) out6[i] = g->slab_phase_ms[i];
+    return MGC_OK;
 }
 
 int mgc_slab_solve_stats(const mgc_graph* g, int64_t* exchanges, int64_t* relabel_rounds, int64_t* push_passes, int64_t* global_relabels)

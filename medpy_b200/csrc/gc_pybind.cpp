@@ -333,6 +333,12 @@ public:
         check(mgc_slab_solve_stats(g_, &a, &b, &c, &d), g_);
         py::dict out;
         out["exchanges"] = a; out["relabel_rounds"] = b; out["push_passes"] = c; out["global_relabels"] = d;
+        double ph[6] = {0, 0, 0, 0, 0, 0};
+        check(mgc_slab_solve_phase_ms(g_, ph), g_);
+        py::dict phase;
+        phase["local_bfs_ms"] = ph[0]; phase["exchange_ms"] = ph[1]; phase["stop_test_ms"] = ph[2]; phase["push_ms"] = ph[3];
+        phase["readout_ms"] = ph[4]; phase["host_blocked_ms"] = ph[5];
+        out["phase_ms"] = phase;
         return out;
     }
 

@@ -412,7 +412,10 @@ def bench_slab(shape, args, rank, world, local_rank):
     roof, roof_mf = rooflines(stats_like, n_local, n, peak, peak_kind)
     roof["kernel"] += " on rank 0's slab"
     roof["share_of_step"] = {"k_build_tile_ms": roof["avg_launch_ms"], "step_ms": ms, "exchanges_cumulative": s.stats["exchanges"],
-                             "note": "slab stepping is asynchronous: push / relabel kernels are not timed individually at N > 1"}
+                             "rank0_phase_ms_last_step": s.stats.get("phase_ms"),
+                             "note": "phase_ms: device time of rank 0's last solve per phase (CUDA events inside mgc_slab_solve): local BFS, "
+                                     "border exchanges (pack + ncclSend/Recv + unpack), stop test (count + all-reduce), push passes, read-out; "
+                                     "host_blocked_ms = host time in the per-round stream synchronisations"}
     roof_mf["ms_per_step"] = None
     return {"value": n / (ms * 1e-3) / 1e6, "ms_per_step": ms, "clocks": r["clocks"], "e2e": e2e,
             "gpu_launches": r["launches"], "roofline": roof, "roofline_maxflow": roof_mf, "energy": energy, "fg_voxels": r["fg_voxels"],
