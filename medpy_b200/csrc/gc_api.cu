@@ -619,6 +619,16 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
         g->n_ctas = 2 * cached_sm_count(device);
         g->use_tiles = true;
         if (const char* sv = getenv("MEDPY_GC_SOLVER")) if (!strcmp(sv, "v0")) g->use_tiles = false;
+        {
+            int coop = 0, nbk = 0;
+            const char* e5 = getenv("MEDPY_GC_BFS");
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+            if ((!e5 || strcmp(e5, "host") != 0) && coop &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbk, k_bfs_coop4, T4_VOX, 0) == cudaSuccess && nbk >= 1)
+                g->coop_bfs_grid = nbk * cached_sm_count(device);
+            else
+                cudaGetLastError();
+        }
         if (const char* e1 = getenv("MEDPY_GC_ITERS")) if (atoi(e1) > 0) g->tile_iters = atoi(e1);
         if (const char* e2 = getenv("MEDPY_GC_PASSES0")) if (atoi(e2) > 0) g->passes0 = atoi(e2);
         if (const char* e3 = getenv("MEDPY_GC_PASSES_MAX")) if (atoi(e3) > 0) g->passes_max = atoi(e3);
@@ -946,13 +956,18 @@ int relabel_tiles_run(mgc_graph* g, int* any, bool want_any = true)
             }
         }
     }
-    if (g->coop_bfs_grid > 0 && g->nd == 3) {
+    if (g->coop_bfs_grid > 0 && g->use_tiles) {
         // all passes in one cooperative launch; the list selector lives in the control block (device side), so the
         // host does not have to synchronise unless the caller wants to know whether anything moved
         CK(cudaMemsetAsync(g->d_tcount + CTL_CURSOR, 0, sizeof(int), g->stream));
         int* it0 = g->rl_items[0]; int* it1 = g->rl_items[1];
-        void* args[] = {&g->L, &g->TL, &g->S.rmask, &g->S.height, &g->rflag, &it0, &it1, &g->d_tcount};
-        CK(cudaLaunchCooperativeKernel((void*)k_bfs_coop, dim3(g->coop_bfs_grid), dim3(TILE_VOX), args, 0, g->stream));
+        if (g->nd == 4) {
+            void* args4[] = {&g->L, &g->TL4, &g->S.rmask, &g->S.height, &g->rflag, &it0, &it1, &g->d_tcount};
+            CK(cudaLaunchCooperativeKernel((void*)k_bfs_coop4, dim3(g->coop_bfs_grid), dim3(T4_VOX), args4, 0, g->stream));
+        } else {
+            void* args[] = {&g->L, &g->TL, &g->S.rmask, &g->S.height, &g->rflag, &it0, &it1, &g->d_tcount};
+            CK(cudaLaunchCooperativeKernel((void*)k_bfs_coop, dim3(g->coop_bfs_grid), dim3(TILE_VOX), args, 0, g->stream));
+        }
         g->st.kernel_launches++;
         g->st.relabel_sweeps++;     // passes are counted on the device (ctl[CTL_RELP]); one launch here
         if (want_any) {
@@ -1326,7 +1341,7 @@ void phase_resolve(mgc_graph* g)
 }
 
 // one border exchange: pack -> grouped send/recv with both neighbours -> unpack, all enqueued on the handle's stream
-int slab_exchange(mgc_graph* g, long long* changed_dev)
+int slab_exchange(mgc_graph* g, long long* changed_dev, bool labels_only)
 {
     Nvtx range("mgc:slab_exchange");
     phase_begin(g, 1);
@@ -1340,20 +1355,22 @@ int slab_exchange(mgc_graph* g, long long* changed_dev)
         if (!have[side]) continue;
         const size_t border = side == 0 ? (size_t)g->L.own0 * P : (size_t)(g->L.own1 - 1) * P;
         const size_t ghost = side == 0 ? border - P : border + P;
-        k_slab_pack<double><<<nb, 256, 0, g->stream>>>(P, g->S.height + border, g->S.excess + ghost, h_send[side], f_send[side]);
+        k_slab_pack<double><<<nb, 256, 0, g->stream>>>(P, g->S.height + border, g->S.excess + ghost, h_send[side], labels_only ? nullptr : f_send[side]);
         g->st.kernel_launches++;
     }
     CK(cudaGetLastError());
+    // relabel rounds exchange labels only (4 B per border voxel); push exchanges add the parked flow (12 B per border voxel)
+    const size_t bytes = labels_only ? g->msg_h_bytes : g->msg_bytes;
     if (g->comm_world > 1) {
         NK(N.GroupStart());
-        if (have[0]) { NK(N.Send(g->msg[0], g->msg_bytes, ncclUint8, g->comm_rank - 1, g->comm, g->stream)); NK(N.Recv(g->msg[2], g->msg_bytes, ncclUint8, g->comm_rank - 1, g->comm, g->stream)); }
-        if (have[1]) { NK(N.Send(g->msg[1], g->msg_bytes, ncclUint8, g->comm_rank + 1, g->comm, g->stream)); NK(N.Recv(g->msg[3], g->msg_bytes, ncclUint8, g->comm_rank + 1, g->comm, g->stream)); }
+        if (have[0]) { NK(N.Send(g->msg[0], bytes, ncclUint8, g->comm_rank - 1, g->comm, g->stream)); NK(N.Recv(g->msg[2], bytes, ncclUint8, g->comm_rank - 1, g->comm, g->stream)); }
+        if (have[1]) { NK(N.Send(g->msg[1], bytes, ncclUint8, g->comm_rank + 1, g->comm, g->stream)); NK(N.Recv(g->msg[3], bytes, ncclUint8, g->comm_rank + 1, g->comm, g->stream)); }
         NK(N.GroupEnd());
     }
     const int32_t* h_lo = have[0] ? (const int32_t*)g->msg[2] : nullptr;
-    const double* f_lo = have[0] ? (const double*)(g->msg[2] + g->msg_h_bytes) : nullptr;
+    const double* f_lo = (have[0] && !labels_only) ? (const double*)(g->msg[2] + g->msg_h_bytes) : nullptr;
     const int32_t* h_hi = have[1] ? (const int32_t*)g->msg[3] : nullptr;
-    const double* f_hi = have[1] ? (const double*)(g->msg[3] + g->msg_h_bytes) : nullptr;
+    const double* f_hi = (have[1] && !labels_only) ? (const double*)(g->msg[3] + g->msg_h_bytes) : nullptr;
     g->slab_exchanges++;
     const int rc_unpack = mgc_slab_unpack(g, h_lo, f_lo, h_hi, f_hi, (int32_t*)changed_dev);
     phase_end(g);
@@ -2217,12 +2234,12 @@ int mgc_slab_pack(mgc_graph* g, int32_t* h_lo, double* f_lo, int32_t* h_hi, doub
     CK(cudaSetDevice(g->device));
     const unsigned P = g->L.plane;
     const unsigned nb = (P + 255u) / 256u;
-    if (g->ghost_lo && h_lo && f_lo) {
+    if (g->ghost_lo && h_lo) {
         const size_t border = (size_t)g->L.own0 * P, ghost = border - P;
         k_slab_pack<double><<<nb, 256, 0, g->stream>>>(P, g->S.height + border, g->S.excess + ghost, h_lo, f_lo);
         g->st.kernel_launches++;
     }
-    if (g->ghost_hi && h_hi && f_hi) {
+    if (g->ghost_hi && h_hi) {
         const size_t border = (size_t)(g->L.own1 - 1) * P, ghost = border + P;
         k_slab_pack<double><<<nb, 256, 0, g->stream>>>(P, g->S.height + border, g->S.excess + ghost, h_hi, f_hi);
         g->st.kernel_launches++;
@@ -2239,7 +2256,7 @@ int mgc_slab_unpack(mgc_graph* g, const int32_t* h_lo, const double* f_lo, const
     const unsigned P = g->L.plane;
     const unsigned nb = (P + 255u) / 256u;
     for (int side = 0; side < 2; ++side) {
-        const bool have = side == 0 ? (g->ghost_lo && h_lo && f_lo) : (g->ghost_hi && h_hi && f_hi);
+        const bool have = side == 0 ? (g->ghost_lo && h_lo) : (g->ghost_hi && h_hi);
         if (!have) continue;
         const int zb = side == 0 ? g->L.own0 : g->L.own1 - 1;
         const int zg = side == 0 ? zb - 1 : zb + 1;
@@ -2398,7 +2415,7 @@ int mgc_slab_solve(mgc_graph* g, double* energy_total)
                 rc = mgc_slab_relabel_relax(g, nullptr);
                 phase_end(g);
                 if (rc) return rc;
-                rc = slab_exchange(g, g->d_stat + k);
+                rc = slab_exchange(g, g->d_stat + k, true);
                 if (rc) return rc;
                 g->slab_relabel_rounds++;
             }
@@ -2421,7 +2438,7 @@ int mgc_slab_solve(mgc_graph* g, double* energy_total)
             rc = mgc_slab_push(g, 1);
             phase_end(g);
             if (rc) return rc;
-            rc = slab_exchange(g, nullptr);
+            rc = slab_exchange(g, nullptr, false);
             if (rc) return rc;
             g->slab_push_passes++;
         }

@@ -9,6 +9,7 @@
 #pragma once
 #include <cooperative_groups.h>
 #include "gc_tiles.cuh"
+#include "gc_tiles4.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -164,6 +165,36 @@ k_bfs_coop(Lattice L, Tiles TL, const uint8_t* __restrict__ rmask, int* __restri
             const int t = fetch_tile(cur, ctl + CTL_CURSOR, &s_slot);
             if (t < 0) break;
             relabel_visit(L, TL, rmask, height, rflag, nxt, t, sh);
+        }
+        grid.sync();
+        if (leader) { ctl[rl_cur] = 0; ctl[CTL_CURSOR] = 0; }
+        rl_cur = 1 - rl_cur;
+        n_rel++;
+        grid.sync();
+    }
+    if (leader) { ctl[CTL_RLCUR] = rl_cur; ctl[CTL_RELP] = n_rel; }
+}
+
+// the same for 4-D lattices (4 x 4 x 8 x 4 tiles): replaces one launch + one host round trip PER PASS (r02 config 4:
+// ~160 passes per solve) by grid barriers inside one cooperative launch
+__global__ void __launch_bounds__(T4_VOX, 3)
+k_bfs_coop4(Lattice L, Tiles4 TL, const uint8_t* __restrict__ rmask, int* __restrict__ height, int* __restrict__ rflag,
+            int* __restrict__ items0, int* __restrict__ items1, int* __restrict__ ctl)
+{
+    __shared__ int sh[H4_VOX];
+    __shared__ int s_slot;
+    cg::grid_group grid = cg::this_grid();
+    const bool leader = blockIdx.x == 0 && threadIdx.x == 0;
+    int rl_cur = ld_ctl(ctl, CTL_RLCUR);
+    int n_rel = 0;
+    for (;;) {
+        if (ld_ctl(ctl, rl_cur) == 0) break;
+        const WorkList cur{rl_cur ? items1 : items0, ctl + rl_cur};
+        const WorkList nxt{rl_cur ? items0 : items1, ctl + (1 - rl_cur)};
+        for (;;) {
+            const int t = fetch_tile(cur, ctl + CTL_CURSOR, &s_slot);
+            if (t < 0) break;
+            relabel_visit4(L, TL, rmask, height, rflag, nxt, t, sh);
         }
         grid.sync();
         if (leader) { ctl[rl_cur] = 0; ctl[CTL_CURSOR] = 0; }

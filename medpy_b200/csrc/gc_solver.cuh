@@ -220,8 +220,10 @@ __global__ void k_slab_pack(unsigned plane, const int* __restrict__ height_borde
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= plane) return;
     h_out[i] = height_border[i];
-    f_out[i] = (double)excess_ghost[i];
-    excess_ghost[i] = 0;
+    if (f_out) {                    // labels-only messages (relabel rounds: nothing was pushed since the last exchange) leave the outbox alone
+        f_out[i] = (double)excess_ghost[i];
+        excess_ghost[i] = 0;
+    }
 }
 
 // unpack: ghost heights <- neighbour's border heights; received flow joins the excess of my border voxel
@@ -235,7 +237,7 @@ __global__ void k_slab_unpack(unsigned plane, int* __restrict__ height_ghost, T*
     if (i >= plane) return;
     int hn = h_in[i];
     if (height_ghost[i] != hn) { height_ghost[i] = hn; if (changed) *changed = 1; }
-    double f = f_in[i];
+    double f = f_in ? f_in[i] : 0.0;
     if (f > 0) {
         excess_border[i] += (T)f;
         cap_border_to_ghost[i] += (T)f;

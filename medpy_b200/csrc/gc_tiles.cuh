@@ -536,7 +536,7 @@ __global__ void k_slab_unpack_tiles(Lattice L, Tiles TL, State<T> S, int z_ghost
         list_push(rflag, rl, tb);
         if (tg != tb) list_push(rflag, rl, tg);
     }
-    const double f = f_in[i];
+    const double f = f_in ? f_in[i] : 0.0;
     if (f > 0) {
         S.excess[vb] += (T)f;
         S.cap[k_border_to_ghost][vb] += (T)f;

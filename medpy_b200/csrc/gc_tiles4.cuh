@@ -165,6 +165,45 @@ __global__ void __launch_bounds__(T4_VOX) k_relabel_reset4(Lattice L, Tiles4 TL,
 // ---------------------------------------------------------------------------------------------------
 // global relabel pass (cf. k_relabel_tile)
 // ---------------------------------------------------------------------------------------------------
+// one tile visit of the 4-D global relabel (cf. relabel_visit): relax inside the tile until nothing changes, write back,
+// list the face neighbours whose halo changed.  `sh` = H4_VOX ints of shared memory.
+__device__ __forceinline__ void relabel_visit4(const Lattice& L, const Tiles4& TL, const uint8_t* __restrict__ rmask,
+                                               int* __restrict__ height, int* __restrict__ rflag, const WorkList& next, int t, int* sh)
+{
+    const Tile4Ctx c = tile4_ctx(L, TL, t);
+    if (threadIdx.x == 0) rflag[t] = 0;
+    const int h0 = load_heights4(L, c, height, sh);
+    const unsigned m = c.own ? rmask[c.v] : 0u;
+    __syncthreads();
+    const int me = h4idx(c.l[0] + 1, c.l[1] + 1, c.l[2] + 1, c.l[3] + 1);
+    int h = h0;
+    for (;;) {
+        int changed = 0;
+        if (m && h > 1) {
+            int best = h;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (m & (1u << k)) {
+                    const int hw = sh[me + ((k & 1) ? t4_hoff(k >> 1) : -t4_hoff(k >> 1))] + 1;
+                    best = hw < best ? hw : best;
+                }
+            }
+            if (best < h) { h = best; sh[me] = h; changed = 1; }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    if (h != h0) {
+        height[c.v] = h;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int ax = k >> 1;
+            const bool edge = (k & 1) ? (c.l[ax] == t4_ext(ax) - 1 && c.tc[ax] + 1 < TL.nt[ax]) : (c.l[ax] == 0 && c.tc[ax] > 0);
+            // only if my new label can lower the voxel across the face (see relabel_visit)
+            if (edge && sh[me + ((k & 1) ? t4_hoff(ax) : -t4_hoff(ax))] > h + 1) list_push(rflag, next, tile4_nbr(TL, t, k));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(T4_VOX) k_relabel_tile4(Lattice L, Tiles4 TL, const uint8_t* __restrict__ rmask,
                                                           int* __restrict__ height, int* __restrict__ rflag,
                                                           WorkList cur, int* __restrict__ cursor, WorkList next)
@@ -174,38 +213,7 @@ __global__ void __launch_bounds__(T4_VOX) k_relabel_tile4(Lattice L, Tiles4 TL, 
     for (;;) {
         const int t = fetch_tile(cur, cursor, &s_slot);
         if (t < 0) break;
-        const Tile4Ctx c = tile4_ctx(L, TL, t);
-        if (threadIdx.x == 0) rflag[t] = 0;
-        const int h0 = load_heights4(L, c, height, sh);
-        const unsigned m = c.own ? rmask[c.v] : 0u;
-        __syncthreads();
-        const int me = h4idx(c.l[0] + 1, c.l[1] + 1, c.l[2] + 1, c.l[3] + 1);
-        int h = h0;
-        for (;;) {
-            int changed = 0;
-            if (m && h > 1) {
-                int best = h;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    if (m & (1u << k)) {
-                        const int hw = sh[me + ((k & 1) ? t4_hoff(k >> 1) : -t4_hoff(k >> 1))] + 1;
-                        best = hw < best ? hw : best;
-                    }
-                }
-                if (best < h) { h = best; sh[me] = h; changed = 1; }
-            }
-            if (!__syncthreads_or(changed)) break;
-        }
-        if (h != h0) {
-            height[c.v] = h;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int ax = k >> 1;
-                const bool edge = (k & 1) ? (c.l[ax] == t4_ext(ax) - 1 && c.tc[ax] + 1 < TL.nt[ax]) : (c.l[ax] == 0 && c.tc[ax] > 0);
-                // only if my new label can lower the voxel across the face (see relabel_visit)
-                if (edge && sh[me + ((k & 1) ? t4_hoff(ax) : -t4_hoff(ax))] > h + 1) list_push(rflag, next, tile4_nbr(TL, t, k));
-            }
-        }
+        relabel_visit4(L, TL, rmask, height, rflag, next, t, sh);
     }
 }
 
