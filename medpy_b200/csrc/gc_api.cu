@@ -562,6 +562,15 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
         for (int i = 0; i < 2 && !rc; ++i) { rc = alloc_buf(g, tb, &p); g->rl_items[i] = (int*)p; }
         for (int i = 0; i < 4 && !rc; ++i) { rc = alloc_buf(g, tb, &p); g->pl_items[i >> 1][i & 1] = (int*)p; }
         if (!rc) { rc = alloc_buf(g, 256, &p); g->d_tcount = (int*)p; }
+        {   // dirty-tile tracking for the partial relabel reset (MEDPY_GC_PARTIAL_RESET=0: off)
+            const char* ed = getenv("MEDPY_GC_PARTIAL_RESET");
+            g->TL.dflag = nullptr; g->TL.ditems = nullptr; g->TL.dcount = nullptr;
+            if (!rc && (!ed || atoi(ed) != 0)) {
+                rc = alloc_buf(g, tb, &p); g->TL.dflag = (int*)p;
+                if (!rc) { rc = alloc_buf(g, tb, &p); g->TL.ditems = (int*)p; }
+                if (!rc) { rc = alloc_buf(g, 64, &p); g->TL.dcount = (int*)p; }
+            }
+        }
         g->n_ctas = 2 * cached_sm_count(device);   // k_push_tile is built for 2 CTAs per SM
         g->use_tiles = true;
         if (const char* sv = getenv("MEDPY_GC_SOLVER")) if (!strcmp(sv, "v0")) g->use_tiles = false;
@@ -847,6 +856,16 @@ int read_tcount(mgc_graph* g, int idx, int* out)
     return MGC_OK;
 }
 
+// forget the dirty tiles (everything is in the reset state: fresh build / init, or a full reset just ran)
+int dirty_clear(mgc_graph* g)
+{
+    if (g->nd == 3 && g->TL.dflag) {
+        CK(cudaMemsetAsync(g->TL.dflag, 0, (size_t)g->TL.ntiles * sizeof(int), g->stream));
+        CK(cudaMemsetAsync(g->TL.dcount, 0, sizeof(int), g->stream));
+    }
+    return MGC_OK;
+}
+
 // first call: solver state + first labels + first worklists in one pass (k_init_tile)
 int init_tiles(mgc_graph* g)
 {
@@ -868,7 +887,7 @@ int init_tiles(mgc_graph* g)
     g->labels_fresh = true;
     g->rl_cur = 0;
     g->sweep_mode = -1;
-    return MGC_OK;
+    return dirty_clear(g);
 }
 
 // exact global relabel by tile-wise relaxation; work is proportional to the tiles whose labels still move.
@@ -886,10 +905,18 @@ int relabel_tiles_begin(mgc_graph* g)
     if (g->nd == 4) {
         k_relabel_reset4<<<g->TL4.ntiles, T4_VOX, 0, g->stream>>>(g->L, g->TL4, g->S.rmask, g->smask, g->S.height, g->rflag, rl(g, 0));
     } else {
-        const unsigned nruns = (unsigned)g->L.dim[0] * (unsigned)g->L.dim[1] * (unsigned)g->TL.nt[2];
-        unsigned grid = (nruns + 255u) / 256u;
-        if (grid > (unsigned)g->n_ctas * 8u) grid = (unsigned)g->n_ctas * 8u;
-        k_relabel_reset<<<grid, 256, 0, g->stream>>>(g->L, g->TL, g->S.rmask, g->S.height, g->rflag, rl(g, 0));
+        if (g->TL.dflag && g->sweep_mode == 0) {
+            // easy instance: only the tiles written since the last reset (labels / sink-link bits) are not in the reset state
+            k_relabel_reset_list<<<g->n_ctas * 2, TILE_VOX, 0, g->stream>>>(g->L, g->TL, g->S.rmask, g->S.height, g->rflag, rl(g, 0));
+            CK(cudaMemsetAsync(g->TL.dcount, 0, sizeof(int), g->stream));
+        } else {
+            const unsigned nruns = (unsigned)g->L.dim[0] * (unsigned)g->L.dim[1] * (unsigned)g->TL.nt[2];
+            unsigned grid = (nruns + 255u) / 256u;
+            if (grid > (unsigned)g->n_ctas * 8u) grid = (unsigned)g->n_ctas * 8u;
+            k_relabel_reset<<<grid, 256, 0, g->stream>>>(g->L, g->TL, g->S.rmask, g->S.height, g->rflag, rl(g, 0));
+            int rcd = dirty_clear(g);
+            if (rcd) return rcd;
+        }
     }
     g->st.kernel_launches++;
     g->rl_cur = 0;
@@ -1912,6 +1939,7 @@ int mgc_build_voxel_graph(mgc_graph* g, const mgc_voxel_terms* t)
 
     CK(cudaMemsetAsync(g->d_tcount, 0, 256, g->stream));
     CK(cudaMemsetAsync(g->d_flags, 0, sizeof(int), g->stream));
+    { int rcd = dirty_clear(g); if (rcd) return rcd; }
     g->pl_sel[0] = g->pl_sel[1] = 0;
     cudaEventRecord(g->ev_b[0], g->stream);
     if (!chunked) {

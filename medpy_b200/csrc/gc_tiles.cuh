@@ -35,7 +35,17 @@
 struct Tiles {
     int nt[3];      // tiles along z, y, x
     int ntiles;
+    // tiles whose labels (or sink-link residual bits) were written since the last relabel reset: only these have to be
+    // put back into the reset state (label 1 where a sink link is residual, HINF elsewhere) before the next BFS
+    int* dflag;     // per tile: already on the dirty list (nullptr: tracking off)
+    int* ditems;    // the dirty list
+    int* dcount;
 };
+
+__device__ __forceinline__ void mark_dirty(const Tiles& TL, int t)
+{
+    if (TL.dflag && atomicExch(&TL.dflag[t], 1) == 0) TL.ditems[atomicAdd(TL.dcount, 1)] = t;
+}
 
 // worklists: items[] + count; kernels consume `cur` through an atomic cursor and append to `next`
 struct WorkList {
@@ -226,6 +236,32 @@ __global__ void __launch_bounds__(256) k_relabel_reset(Lattice L, Tiles TL, cons
     relabel_reset_body(L, TL, rmask, height, rflag, rl);
 }
 
+// the same reset restricted to the DIRTY tiles (Tiles::ditems): every other tile is still in the reset state, so an easy
+// instance (regional term: the BFS only ever labels the few tiles around the objects) pays for those tiles instead of a
+// 5 B/voxel pass over the lattice (r02 launch list: 2 x 0.146 ms of a 4.6 ms step at 512^3).  Persistent CTAs of one
+// tile each; clears the dirty flags it consumes (the host zeroes the count afterwards).
+__global__ void __launch_bounds__(TILE_VOX) k_relabel_reset_list(Lattice L, Tiles TL, const uint8_t* __restrict__ rmask,
+                                                                 int* __restrict__ height, int* __restrict__ rflag, WorkList rl)
+{
+    const int n = *(volatile int*)TL.dcount;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int t = TL.ditems[i];
+        const TileCtx c = tile_ctx(L, TL, t);
+        int needs = 0;
+        if (c.inb) {
+            const unsigned m = rmask[c.v];
+            const int h = (c.own && (m & RM_SINK)) ? 1 : MGC_HINF;
+            height[c.v] = h;
+            needs = (c.own && (m & 0x3fu) != 0 && h == MGC_HINF) ? 1 : 0;
+        }
+        const int any = __syncthreads_or(needs);
+        if (threadIdx.x == 0) {
+            TL.dflag[t] = 0;
+            if (any) list_push(rflag, rl, t);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // global relabel pass: persistent CTAs over the current worklist
 // ---------------------------------------------------------------------------------------------------
@@ -267,6 +303,10 @@ __device__ __forceinline__ void relabel_visit(const Lattice& L, const Tiles& TL,
         if (c.ly == TILE - 1 && c.ty + 1 < TL.nt[1] && sh[me + hoff<3>()] > h + 1) list_push(rflag, next, tile_nbr(TL, t, 3));
         if (c.lx == 0 && c.tx > 0 && sh[me + hoff<4>()] > h + 1) list_push(rflag, next, tile_nbr(TL, t, 4));
         if (c.lx == TILE - 1 && c.tx + 1 < TL.nt[2] && sh[me + hoff<5>()] > h + 1) list_push(rflag, next, tile_nbr(TL, t, 5));
+    }
+    if (TL.dflag) {                          // labels of this tile changed: it has to be reset before the next BFS
+        const int chg = __syncthreads_or(h != h0 ? 1 : 0);
+        if (chg && threadIdx.x == 0) mark_dirty(TL, t);
     }
 }
 
@@ -424,6 +464,10 @@ __device__ __forceinline__ void push_visit_staged(const Lattice& L, const Tiles&
     }
     const int still = (c.own && e > 0 && h < MGC_HINF) ? 1 : 0;
     if (__syncthreads_or(still) && tid == 0) list_push(pflag, self_next, t);
+    if (TL.dflag) {                          // a label or a sink-link residual bit of this tile changed
+        const int chg = __syncthreads_or((c.inb && (h != h0 || (dirty & 128u))) ? 1 : 0);
+        if (chg && tid == 0) mark_dirty(TL, t);
+    }
 }
 
 template <typename T>
@@ -532,6 +576,7 @@ __global__ void k_slab_unpack_tiles(Lattice L, Tiles TL, State<T> S, int z_ghost
     const int hn = h_in[i];
     if (S.height[vg] != hn) {
         S.height[vg] = hn;
+        mark_dirty(TL, tg);
         if (changed) *changed = 1;
         list_push(rflag, rl, tb);
         if (tg != tb) list_push(rflag, rl, tg);
