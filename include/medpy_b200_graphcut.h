@@ -114,6 +114,9 @@ int mgc_abi_version(void);
  * the block to the pool. */
 int mgc_host_alloc(size_t bytes, void** out);
 void mgc_host_free(void* p);
+/* Device and pinned-host blocks are cached process-wide (a 1024^3 handle holds 84 GB; its blocks stay cached for the next
+ * graph after mgc_destroy).  mgc_trim_pools returns every cached block to the driver; live handles keep theirs. */
+int mgc_trim_pools(void);
 /* Options.  MGC_OPT_DEFER_WEIGHT_CHECK (default 0): mgc_add_boundary on a HOST image does not wait for its kernel to
  * report non-positive weights; the verdict (MGC_E_WEIGHT) is delivered by the next call on the handle instead (terms,
  * markers, maxflow, mgc_check).  graph_from_voxels switches it on because it always adds the markers right after the

@@ -1675,6 +1675,25 @@ void mgc_host_free(void* p)
     g_host_live.erase(it);
 }
 
+// Give cached blocks back to the driver: every device block of the size-keyed pool (all devices) and every pinned host block
+// that is not handed out.  Handles that are alive keep what they hold.
+int mgc_trim_pools(void)
+{
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto& kv : g_pool) {
+        if (kv.second.empty()) continue;
+        cudaSetDevice(kv.first.first);
+        for (void* p : kv.second) cudaFree(p);
+        kv.second.clear();
+    }
+    cudaSetDevice(cur);
+    for (auto& kv : g_host_pool) { for (void* p : kv.second) cudaFreeHost(p); kv.second.clear(); }
+    cudaGetLastError();
+    return MGC_OK;
+}
+
 int mgc_set_option(mgc_graph* g, int32_t option, int64_t value)
 {
     if (!g) return MGC_E_ARG;

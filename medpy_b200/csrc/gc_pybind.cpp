@@ -552,6 +552,7 @@ py::array_t<float> gradient_magnitude_prewitt(const py::object& image, int devic
 
 PYBIND11_MODULE(_mgc, m)
 {
+    m.def("trim_pools", []() { mgc_trim_pools(); }, "Return every cached device / pinned block to the driver (live graphs keep theirs).");
     m.def("gradient_magnitude_prewitt", &gradient_magnitude_prewitt, py::arg("image"), py::arg("device") = -1);
     m.doc() = "pybind11 binding of libmedpy_b200_gc (B200 voxel graph-cut C ABI)";
     m.attr("ABI_VERSION") = mgc_abi_version();
