@@ -411,7 +411,10 @@ def bench_slab(shape, args, rank, world, local_rank):
     stats_like = [{"ms_boundary": b, "ms_relabel": 0.0, "ms_push": 0.0, "ms_solve": 0.0, "ms_readout": 0.0} for b in r["build_ms"]]
     roof, roof_mf = rooflines(stats_like, n_local, n, peak, peak_kind)
     roof["kernel"] += " on rank 0's slab"
+    phases_all = [None] * world
+    dist.all_gather_object(phases_all, s.stats.get("phase_ms"))
     roof["share_of_step"] = {"k_build_tile_ms": roof["avg_launch_ms"], "step_ms": ms, "exchanges_cumulative": s.stats["exchanges"],
+                             "phase_ms_last_step_per_rank": phases_all,
                              "rank0_phase_ms_last_step": s.stats.get("phase_ms"),
                              "note": "phase_ms: device time of rank 0's last solve per phase (CUDA events inside mgc_slab_solve): local BFS, "
                                      "border exchanges (pack + ncclSend/Recv + unpack), stop test (count + all-reduce), push passes, read-out; "
