@@ -194,7 +194,7 @@ struct mgc_graph {
     int sweep_mode = -1;               // decided at the first relabel of a solve: 1 = hard instance (sweep at every relabel), 0 = worklist BFS only
     bool use_sweeps = true;
     int sweep_frac = 8;                // sweep when pending tiles > ntiles / sweep_frac
-    int sweep_rounds_max = 4;
+    int sweep_rounds_max = 2;          // measured: a third round never pays for itself on configs 2 / 4 / 5
     int sweep_done_frac = 16;          // hand over to the worklist BFS when violating tiles <= ntiles / sweep_done_frac (measured best on configs 2 / 4)
 
     // tuning
@@ -565,6 +565,14 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
         {   // dirty-tile tracking for the partial relabel reset (MEDPY_GC_PARTIAL_RESET=0: off)
             const char* ed = getenv("MEDPY_GC_PARTIAL_RESET");
             g->TL.dflag = nullptr; g->TL.ditems = nullptr; g->TL.dcount = nullptr;
+            g->TL.schg = nullptr; g->TL.sweep_stamp = 0;
+            {   // sweep marks (MEDPY_GC_SWEEP_CHECK=1: the exhaustive fixed-point check kernel instead)
+                const char* es = getenv("MEDPY_GC_SWEEP_CHECK");
+                if (!rc && (!es || atoi(es) == 0)) {
+                    rc = alloc_buf(g, tb, &p); g->TL.schg = (int*)p;
+                    if (!rc && cudaMemset(p, 0, tb) != cudaSuccess) { cudaGetLastError(); g->TL.schg = nullptr; }
+                }
+            }
             if (!rc && (!ed || atoi(ed) != 0)) {
                 rc = alloc_buf(g, tb, &p); g->TL.dflag = (int*)p;
                 if (!rc) { rc = alloc_buf(g, tb, &p); g->TL.ditems = (int*)p; }
@@ -931,13 +939,15 @@ int relabel_tiles_begin(mgc_graph* g)
 int relabel_sweep_round(mgc_graph* g, int* pending)
 {
     const int last = g->nd - 1;
+    if (g->nd == 3 && g->TL.schg) g->TL.sweep_stamp++;        // marks of this round (the array is never cleared)
     for (int a = 0; a < last; ++a) {
         if (g->L.dim[a] < 2) continue;
         const unsigned nlines = g->L.n / (unsigned)g->L.dim[a];
-        k_sweep_axis<<<(nlines + 255u) / 256u, 256, 0, g->stream>>>(g->L, g->S.rmask, g->S.height, a);
+        k_sweep_axis<<<(nlines + 255u) / 256u, 256, 0, g->stream>>>(g->L, g->TL, g->S.rmask, g->S.height, a);
         g->st.kernel_launches++;
     }
-    if (g->L.dim[last] >= 2 && g->L.dim[last] <= SWEEP_SHORT) {
+    const bool marks = g->nd == 3 && g->TL.schg;      // the short-row kernel does not mark tiles: 3-D lattices use the general one
+    if (g->L.dim[last] >= 2 && g->L.dim[last] <= SWEEP_SHORT && !marks) {
         const unsigned nrows = g->L.n / (unsigned)g->L.dim[last];
         k_sweep_rows_short<<<(nrows + 255u) / 256u, 256, 0, g->stream>>>(g->L, g->S.rmask, g->S.height);
         g->st.kernel_launches++;
@@ -946,12 +956,13 @@ int relabel_sweep_round(mgc_graph* g, int* pending)
         unsigned grid = (nrows + SWEEP_WARPS - 1) / SWEEP_WARPS;
         const unsigned cap = (unsigned)cached_sm_count(g->device) * 16u;
         if (grid > cap) grid = cap;
-        k_sweep_rows<<<grid, 32 * SWEEP_WARPS, 0, g->stream>>>(g->L, g->S.rmask, g->S.height);
+        k_sweep_rows<<<grid, 32 * SWEEP_WARPS, 0, g->stream>>>(g->L, g->TL, g->S.rmask, g->S.height);
         g->st.kernel_launches++;
     }
     CK(cudaMemsetAsync(g->d_tcount, 0, 2 * sizeof(int), g->stream));
     CK(cudaMemsetAsync(g->rflag, 0, (size_t)g->TL.ntiles * sizeof(int), g->stream));
     if (g->nd == 4) k_relabel_check4<<<nblocks(g), 256, 0, g->stream>>>(g->L, g->TL4, g->S.rmask, g->S.height, g->rflag, rl(g, 0));
+    else if (g->TL.schg) k_sweep_list<<<(g->TL.ntiles + 255) / 256, 256, 0, g->stream>>>(g->TL, g->rflag, rl(g, 0));
     else            k_relabel_check<<<nblocks(g), 256, 0, g->stream>>>(g->L, g->TL, g->S.rmask, g->S.height, g->rflag, rl(g, 0));
     g->st.kernel_launches++;
     g->rl_cur = 0;

@@ -40,6 +40,9 @@ struct Tiles {
     int* dflag;     // per tile: already on the dirty list (nullptr: tracking off)
     int* ditems;    // the dirty list
     int* dcount;
+    // directional sweeps (gc_sweep.cuh): schg[t] = stamp of the last sweep round that lowered a label inside tile t
+    int* schg;
+    int sweep_stamp;
 };
 
 __device__ __forceinline__ void mark_dirty(const Tiles& TL, int t)
