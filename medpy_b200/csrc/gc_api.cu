@@ -194,6 +194,7 @@ struct mgc_graph {
     int sweep_mode = -1;               // decided at the first relabel of a solve: 1 = hard instance (sweep at every relabel), 0 = worklist BFS only
     bool use_sweeps = true;
     int sweep_frac = 8;                // sweep when pending tiles > ntiles / sweep_frac
+    int sweep_rounds_min = 2;          // rounds before the first fixed-point check (MEDPY_GC_SWEEP_MIN_ROUNDS)
     int sweep_rounds_max = 2;          // measured: a third round never pays for itself on configs 2 / 4 / 5
     int sweep_done_frac = 16;          // hand over to the worklist BFS when violating tiles <= ntiles / sweep_done_frac (measured best on configs 2 / 4)
 
@@ -591,6 +592,7 @@ int create_impl(int32_t ndim, const int64_t* shape, int64_t z0, int64_t z1, bool
         if (const char* e7 = getenv("MEDPY_GC_SWEEP")) g->use_sweeps = atoi(e7) != 0;
         if (const char* e8 = getenv("MEDPY_GC_SWEEP_FRAC")) if (atoi(e8) > 0) g->sweep_frac = atoi(e8);
         if (const char* e9 = getenv("MEDPY_GC_SWEEP_ROUNDS")) if (atoi(e9) > 0) g->sweep_rounds_max = atoi(e9);
+        if (const char* e11 = getenv("MEDPY_GC_SWEEP_MIN_ROUNDS")) if (atoi(e11) > 0) g->sweep_rounds_min = atoi(e11);
         if (const char* e10 = getenv("MEDPY_GC_SWEEP_DONE_FRAC")) if (atoi(e10) > 0) g->sweep_done_frac = atoi(e10);
         {
             const char* e6 = getenv("MEDPY_GC_TMA");
@@ -938,7 +940,7 @@ int relabel_tiles_begin(mgc_graph* g)
 // run passes until the current worklist is empty; *any = 1 if any tile was visited
 // one round of directional sweeps (both directions of every axis), then the list of tiles that are not at the fixed
 // point yet (gc_sweep.cuh); *pending = number of such tiles (host synchronisation)
-int relabel_sweep_round(mgc_graph* g, int* pending)
+int relabel_sweep_round(mgc_graph* g, int* pending, bool with_check)
 {
     const int last = g->nd - 1;
     if (g->nd == 3 && g->TL.schg) g->TL.sweep_stamp++;        // marks of this round (the array is never cleared)
@@ -961,6 +963,8 @@ int relabel_sweep_round(mgc_graph* g, int* pending)
         k_sweep_rows<<<grid, 32 * SWEEP_WARPS, 0, g->stream>>>(g->L, g->TL, g->S.rmask, g->S.height);
         g->st.kernel_launches++;
     }
+    g->st.relabel_sweeps++;
+    if (!with_check) { CK(cudaGetLastError()); return MGC_OK; }     // an early round: the next one follows without a verdict
     CK(cudaMemsetAsync(g->d_tcount, 0, 2 * sizeof(int), g->stream));
     CK(cudaMemsetAsync(g->rflag, 0, (size_t)g->TL.ntiles * sizeof(int), g->stream));
     if (g->nd == 4) k_relabel_check4<<<nblocks(g), 256, 0, g->stream>>>(g->L, g->TL4, g->S.rmask, g->S.height, g->rflag, rl(g, 0));
@@ -970,7 +974,6 @@ int relabel_sweep_round(mgc_graph* g, int* pending)
     g->rl_cur = 0;
     CK(cudaMemsetAsync(g->d_tcount + CTL_RLCUR, 0, sizeof(int), g->stream));
     CK(cudaGetLastError());
-    g->st.relabel_sweeps++;
     return read_tcount(g, 0, pending);
 }
 
@@ -987,9 +990,13 @@ int relabel_tiles_run(mgc_graph* g, int* any, bool want_any = true)
         if (pending > g->TL.ntiles / g->sweep_frac) {
             *any = 1;
             int prev = g->TL.ntiles + 1;
+            const int rmin = g->sweep_rounds_min < g->sweep_rounds_max ? g->sweep_rounds_min : g->sweep_rounds_max;
             for (int r = 0; r < g->sweep_rounds_max; ++r) {
-                rc = relabel_sweep_round(g, &pending);
+                // the first rounds run without the 5 B/voxel fixed-point check: nobody would act on its verdict
+                const bool check = r + 1 >= rmin;
+                rc = relabel_sweep_round(g, &pending, check);
                 if (rc) return rc;
+                if (!check) continue;
                 if (pending <= g->TL.ntiles / g->sweep_done_frac) break;
                 if ((long long)pending * 4 > (long long)prev * 3) break;      // a round that clears < 25 %: the rest is local detail
                 prev = pending;
