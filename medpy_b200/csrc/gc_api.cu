@@ -295,6 +295,15 @@ int ensure_scratch(mgc_graph* g, Buf& b, size_t bytes)
 template <typename E>
 int gather_launch(mgc_graph* g, const char* src, const Strides4& st, E* dst)
 {
+    // exact Fortran order over a 3-D lattice (the layout medpy.io.load hands out): coalesced tiled transpose
+    const int Z = g->L.dim[0], Y = g->L.dim[1], X = g->L.dim[2];
+    if (g->nd == 3 && Z > 1 && X > 1 && Y <= 65535 && (Z + 31) / 32 <= 65535 &&
+        st.s[0] == (long long)sizeof(E) && (Y == 1 || st.s[1] == (long long)sizeof(E) * Z) && st.s[2] == (long long)sizeof(E) * Z * Y) {
+        const dim3 grid((unsigned)((X + 31) / 32), (unsigned)Y, (unsigned)((Z + 31) / 32));
+        k_gather_fortran3<E><<<grid, 256, 0, g->stream>>>(Z, Y, X, reinterpret_cast<const E*>(src), dst);
+        g->st.kernel_launches++;
+        return MGC_OK;
+    }
     if (g->nd == 3) k_gather<E, 3><<<nblocks(g), 256, 0, g->stream>>>(g->L, src, st, dst);
     else            k_gather<E, 4><<<nblocks(g), 256, 0, g->stream>>>(g->L, src, st, dst);
     g->st.kernel_launches++;

@@ -56,6 +56,30 @@ __global__ void k_gather(Lattice L, const char* __restrict__ src, Strides4 st, E
     dst[v] = *reinterpret_cast<const E*>(src + off);
 }
 
+// Fortran-ordered 3-D input (what medpy.io.load returns, io/load.py:125-127): logical axis 0 is the FASTEST in memory,
+// so the plain gather above reads one element per 128-byte line.  Tiled transpose instead: for a fixed logical y, a
+// 32 x 32 tile of the (z, x) plane is read with z fastest (coalesced in the source) into shared memory and written with x
+// fastest (coalesced in the destination).  src element (z, y, x) sits at z + Z * (y + Y * x); dst is C order.
+template <typename E>
+__global__ void __launch_bounds__(256) k_gather_fortran3(int Z, int Y, int X, const E* __restrict__ src, E* __restrict__ dst)
+{
+    __shared__ E tile[32][33];
+    const int y = blockIdx.y;
+    const int z0 = blockIdx.z * 32, x0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8 threads
+#pragma unroll
+    for (int r = 0; r < 32; r += 8) {
+        const int x = x0 + ty + r, z = z0 + tx;
+        if (x < X && z < Z) tile[ty + r][tx] = src[(size_t)z + (size_t)Z * ((size_t)y + (size_t)Y * (size_t)x)];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 32; r += 8) {
+        const int z = z0 + ty + r, x = x0 + tx;
+        if (x < X && z < Z) dst[((size_t)z * Y + y) * (size_t)X + x] = tile[tx][ty + r];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K0: global min / max (difference_linear: |max - min| in the input dtype, energy_voxel.py:174;
 //     maximum_linear: max |x| in the input dtype, energy_voxel.py:99)
