@@ -4,7 +4,7 @@ import os
 import numpy
 
 from ..core import ImageLoadingError, Logger
-from . import _metaimage
+from . import _metaimage, _nifti
 from .header import Header
 
 
@@ -20,8 +20,10 @@ def load(image):
             spacing, offset, nchan = [1.0] * zyx.ndim, [0.0] * zyx.ndim, 1
         elif ext in (".mha", ".mhd"):
             zyx, spacing, offset, nchan = _metaimage.read(image)
+        elif ext == ".nii" or image.lower().endswith(".nii.gz"):
+            zyx, spacing, offset, nchan = _nifti.read(image)
         else:
-            raise ImageLoadingError("Only .npy and uncompressed MetaImage (.mha/.mhd) are supported without SimpleITK.")
+            raise ImageLoadingError("Only .npy, uncompressed MetaImage (.mha/.mhd) and NIfTI-1 (.nii/.nii.gz) are supported without SimpleITK.")
     except ImageLoadingError:
         raise
     except Exception as e:  # noqa: BLE001

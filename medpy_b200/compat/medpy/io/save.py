@@ -4,7 +4,7 @@ import os
 import numpy
 
 from ..core import ImageSavingError, Logger
-from . import _metaimage
+from . import _metaimage, _nifti
 
 
 def save(arr, filename, hdr=False, force=True, use_compression=False):
@@ -26,8 +26,12 @@ def save(arr, filename, hdr=False, force=True, use_compression=False):
             spacing = hdr.get_voxel_spacing() if hdr else None
             offset = hdr.get_offset() if hdr else None
             _metaimage.write(filename, zyx, spacing, offset)
+        elif ext == ".nii" or filename.lower().endswith(".nii.gz"):
+            spacing = hdr.get_voxel_spacing() if hdr else None
+            offset = hdr.get_offset() if hdr else None
+            _nifti.write(filename, zyx, spacing, offset)
         else:
-            raise ImageSavingError("Only .npy and MetaImage (.mha/.mhd) are supported without SimpleITK.")
+            raise ImageSavingError("Only .npy, MetaImage (.mha/.mhd) and NIfTI-1 (.nii/.nii.gz) are supported without SimpleITK.")
     except ImageSavingError:
         raise
     except Exception as e:  # noqa: BLE001

@@ -11,7 +11,7 @@ COMPAT = os.path.join(ROOT, "medpy_b200", "compat")
 REF_CLI = "/root/reference/bin/medpy_graphcut_voxel.py"
 
 
-def _write_case(tmp_path, shape=(12, 10, 9)):
+def _write_case(tmp_path, shape=(12, 10, 9), ext=".mha"):
     sys.path.insert(0, COMPAT)
     try:
         from medpy.io import save, Header
@@ -23,7 +23,7 @@ def _write_case(tmp_path, shape=(12, 10, 9)):
     img_xyz = numpy.ascontiguousarray(vol["image"]).T
     markers = (vol["fg"].astype(numpy.uint8) + 2 * vol["bg"].astype(numpy.uint8)).T
     hdr = Header(spacing=(1.0, 1.0, 2.0), offset=(0.0, 0.0, 0.0))
-    ip, mp = str(tmp_path / "img.mha"), str(tmp_path / "markers.mha")
+    ip, mp = str(tmp_path / ("img" + ext)), str(tmp_path / ("markers" + ext))
     save(img_xyz, ip, hdr, True)
     save(markers, mp, hdr, True)
     return vol, ip, mp
@@ -70,10 +70,11 @@ def test_reference_cli_runs_unchanged_up_to_the_device(tmp_path):
 
 
 @pytest.mark.gpu
-def test_own_cli_matches_oracle(tmp_path):
+@pytest.mark.parametrize("ext", [".mha", ".nii.gz"])
+def test_own_cli_matches_oracle(tmp_path, ext):
     from oracle import energy_terms as et, solvers
-    vol, ip, mp = _write_case(tmp_path, shape=(20, 16, 18))
-    out = str(tmp_path / "out.mha")
+    vol, ip, mp = _write_case(tmp_path, shape=(20, 16, 18), ext=ext)
+    out = str(tmp_path / ("out" + ext))
     r = subprocess.run([sys.executable, os.path.join(ROOT, "medpy_b200", "cli", "graphcut_voxel.py"), "15.0", ip, mp, out,
                         "--boundary", "diff_exp", "-s", "-f"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
