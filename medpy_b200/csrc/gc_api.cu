@@ -1484,10 +1484,10 @@ bool make_block_map(mgc_graph* g, const void* ptr, int dtype, CUtensorMap* out)
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename E, int FN, int USE_MAX, int SPACING>
+template <typename E, int FN, int USE_MAX, int SPACING, int TIN = 0>
 int build_launch_inst(mgc_graph* g, const BuildMaps& imap, const BuildArgs& A, const BoundaryParams& P, int nz_layers)
 {
-    auto kern = k_build_tile<E, double, FN, USE_MAX, SPACING>;
+    auto kern = k_build_tile<E, double, FN, USE_MAX, SPACING, TIN>;
     const size_t smem = build_smem_bytes<E>();
     static bool attr_done = false;       // per instantiation
     if (!attr_done) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done = true; }
@@ -1504,6 +1504,15 @@ int build_launch(mgc_graph* g, const BuildMaps& imap, const BuildArgs& A, const 
 {
     if constexpr (!std::is_integral<E>::value) {
         if (P.fn == 1 && P.inv_spacing_on == 0.0) {
+            if constexpr (std::is_same<E, float>::value) {
+                // float32 image + float32 probability map + byte markers, everything staged by TMA: the compile-time variant
+                const bool fast = A.use_tma && A.prob && !A.prob_f64 && A.compute_f32 && A.tma_prob && A.tma_mark == 3 &&
+                                  !A.fg_bits && !A.bg_bits && A.dbg == 0;
+                if (fast) {
+                    if (P.use_max) return build_launch_inst<E, 1, 1, 0, 1>(g, imap, A, P, nz_layers);
+                    return build_launch_inst<E, 1, 0, 0, 1>(g, imap, A, P, nz_layers);
+                }
+            }
             if (P.use_max) return build_launch_inst<E, 1, 1, 0>(g, imap, A, P, nz_layers);
             return build_launch_inst<E, 1, 0, 0>(g, imap, A, P, nz_layers);
         }

@@ -174,6 +174,28 @@ __device__ __forceinline__ double exp_neg(double t)
     return (t != t) ? t : res;
 }
 
+// The same function for arguments known to lie in [0, 700] (no NaN): none of the range handling, bit-identical results
+// (y = -t needs no clamp, n >= -1010 keeps the scaled result normal, so the exponent-field add is exact and the result is
+// positive -- no DBL_MIN clamp either).  Callers establish the range for the whole warp with one vote.
+__device__ __forceinline__ double exp_neg_inrange(double t)
+{
+    const double y = -t;
+    const double n = rint(__dmul_rn(y, 1.4426950408889634));
+    double r = __fma_rn(-n, 6.93147180369123816490e-01, y);
+    r = __fma_rn(-n, 1.90821492927058770002e-10, r);
+    double p = EXPN_C[13];
+#pragma unroll
+    for (int k = 12; k >= 0; --k) p = __fma_rn(p, r, EXPN_C[k]);
+    return __hiloint2double(__double2hiint(p) + ((int)n << 20), __double2loint(p));
+}
+
+// argument of the exponential term, exactly as g_weight<1> forms it
+__device__ __forceinline__ double exp_term_arg(const BoundaryParams& P, double x)
+{
+    return (P.inv_sigma2 > 0.0 && P.inv_sigma2 < 1e300) ? __dmul_rn(__dmul_rn(x, x), P.inv_sigma2)
+                                                        : __ddiv_rn(__dmul_rn(x, x), P.sigma);
+}
+
 // FN >= 0 fixes the term at compile time (the specialised kernels of the common cases), FN < 0 reads it from P
 template <int FN>
 __device__ __forceinline__ double g_weight(const BoundaryParams& P, double x)
