@@ -2021,7 +2021,7 @@ int mgc_build_voxel_graph(mgc_graph* g, const mgc_voxel_terms* t)
                 CK(cudaStreamWaitEvent(g->stream, g->ev_chunk[c & 1], 0));
                 A.z_tile0 = prev_l0;
                 rc = build_launch_dtype(g, t->image->dtype, imap, A, P, prev_nl);
-                if (rc) return rc;
+                if (rc) { cudaStreamSynchronize(g->up_stream); return rc; }     // the host arrays are borrowed: no copy may outlive the call
             }
             if (t->prob) CK(cudaMemcpyAsync((char*)g->scratch[0].p + v0 * es_prob, (const char*)t->prob->data + v0 * es_prob, nv * es_prob, cudaMemcpyHostToDevice, g->up_stream));
             if (has_bits) {
@@ -2043,7 +2043,7 @@ int mgc_build_voxel_graph(mgc_graph* g, const mgc_voxel_terms* t)
         CK(cudaStreamWaitEvent(g->stream, g->ev_up, 0));
         A.z_tile0 = prev_l0;
         rc = build_launch_dtype(g, t->image->dtype, imap, A, P, prev_nl);
-        if (rc) return rc;
+        if (rc) { cudaStreamSynchronize(g->up_stream); return rc; }
         CK(cudaEventSynchronize(g->ev_up));       // the host arrays are only borrowed for this call
     }
     cudaEventRecord(g->ev_b[1], g->stream);
